@@ -1,0 +1,188 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports ``renderers``, ``losses``, ``environment`` and ``utils`` from
+``/root/reference/development/multiImage_pytorch`` (an empty ``pyredner`` module is put into
+``sys.modules`` because ``renderers.py:4`` imports it unconditionally; only the out-of-scope
+``RednerRenderer`` uses it), evaluates ``LocalRenderer.render`` and ``RenderingLoss`` in fp32
+and - through ``torch.set_default_dtype(torch.float64)`` - in fp64 on small seeded inputs and
+writes ``*.npz`` files.  Nothing from the reference is copied; only its outputs are stored.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/development/multiImage_pytorch"
+
+
+def load_reference():
+    sys.modules.setdefault("pyredner", types.ModuleType("pyredner"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import environment as ref_env      # noqa: E402
+    import losses as ref_losses        # noqa: E402
+    import renderers as ref_renderers  # noqa: E402
+    import utils as ref_utils          # noqa: E402
+    return ref_env, ref_losses, ref_renderers, ref_utils
+
+
+def synthetic_maps(batch, size, seed, stress=False):
+    """Same distributions as SURVEY.md §8(d): unit upper-hemisphere normals, diffuse/specular
+    U(0,1), roughness U(0.1,1) replicated x3.  ``stress`` adds the hard cases of §8(c)."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    xy = torch.randn(batch, 2, size, size, generator=g) * 0.3
+    n = torch.cat((xy, torch.ones(batch, 1, size, size)), dim=1)
+    n = n / n.norm(dim=1, keepdim=True)
+    d = torch.rand(batch, 3, size, size, generator=g)
+    s = torch.rand(batch, 3, size, size, generator=g)
+    if not stress:
+        r = (torch.rand(batch, 1, size, size, generator=g) * 0.9 + 0.1).repeat(1, 3, 1, 1)
+    else:
+        r = torch.rand(batch, 3, size, size, generator=g)           # independent channels
+        kill = torch.rand(batch, 3, size, size, generator=g)
+        r = torch.where(kill < 0.01, torch.zeros_like(r), r)        # exact zeros
+        r = torch.where((kill >= 0.01) & (kill < 0.02), r * 1e-3, r)  # below the 1e-3 clamp
+        scale = 0.5 + torch.rand(batch, 1, size, size, generator=g)  # non-unit normals
+        flip = torch.rand(batch, 1, size, size, generator=g) < 0.05  # a few facing away
+        n = n * scale
+        n[:, 2:3] = torch.where(flip, -n[:, 2:3], n[:, 2:3])
+    return torch.cat((n, d, r, s), dim=1).contiguous()
+
+
+def scenes_from_configs(ref_env, cfg_row):
+    """[N,9] fp32 -> list of reference Scene objects with python-float lists (valid under
+    either default dtype)."""
+    out = []
+    for k in range(cfg_row.shape[0]):
+        v = [float(x) for x in cfg_row[k]]
+        out.append(ref_env.Scene(ref_env.Camera(v[0:3]), ref_env.Light(v[3:6], v[6:9])))
+    return out
+
+
+def sample_configs(ref_env, seed, batch, n_random, n_specular):
+    """Reference sampler, reference draw order (losses.py:35), packed to [B,N,9] fp32."""
+    torch.manual_seed(seed)
+    rows = []
+    for _ in range(batch):
+        scenes = ref_env.generate_random_scenes(n_random) + ref_env.generate_specular_scenes(n_specular)
+        rows.append(torch.stack([torch.cat((torch.as_tensor(s.camera.pos, dtype=torch.float32),
+                                            torch.as_tensor(s.light.pos, dtype=torch.float32),
+                                            torch.as_tensor(s.light.color, dtype=torch.float32)))
+                                 for s in scenes]))
+    return torch.stack(rows)
+
+
+class _FixedScenes:
+    """Replaces the two sampler functions of the reference's ``environment`` module so that
+    ``RenderingLoss.forward`` consumes pre-recorded configurations."""
+
+    def __init__(self, ref_env, configs, n_random):
+        self.ref_env, self.configs, self.n_random, self.b = ref_env, configs, n_random, 0
+
+    def random(self, count):
+        assert count == self.n_random
+        return scenes_from_configs(self.ref_env, self.configs[self.b, :count])
+
+    def specular(self, count):
+        row = self.configs[self.b, self.n_random:]
+        assert count == row.shape[0]
+        self.b += 1
+        return scenes_from_configs(self.ref_env, row)
+
+
+def reference_loss(ref, dtype, inp, tgt, configs, n_random):
+    ref_env, ref_losses, ref_renderers, _ = ref
+    torch.set_default_dtype(dtype)
+    keep = (ref_env.generate_random_scenes, ref_env.generate_specular_scenes)
+    try:
+        fixed = _FixedScenes(ref_env, configs, n_random)
+        ref_env.generate_random_scenes, ref_env.generate_specular_scenes = fixed.random, fixed.specular
+        loss_mod = ref_losses.RenderingLoss(ref_renderers.LocalRenderer())
+        loss_mod.random_configuration_count = n_random
+        loss_mod.specular_configuration_count = configs.shape[1] - n_random
+        x = inp.to(dtype).clone().requires_grad_(True)
+        loss = loss_mod(x, tgt.to(dtype))
+        loss.backward()
+        renderer = ref_renderers.LocalRenderer()
+        renders = torch.stack([torch.cat([renderer.render(s, x.detach()[b])
+                                          for s in scenes_from_configs(ref_env, configs[b])])
+                               for b in range(x.shape[0])])
+        return loss.detach().numpy(), x.grad.numpy(), renders.numpy()
+    finally:
+        ref_env.generate_random_scenes, ref_env.generate_specular_scenes = keep
+        torch.set_default_dtype(torch.float32)
+
+
+def main():
+    ref = load_reference()
+    ref_env, ref_losses, ref_renderers, ref_utils = ref
+
+    # 1. sampler pins -------------------------------------------------------------------
+    np.savez(os.path.join(HERE, "scenes.npz"),
+             seed313_b4_r3_s6=sample_configs(ref_env, 313, 4, 3, 6).numpy(),
+             seed7_b2_r9_s18=sample_configs(ref_env, 7, 2, 9, 18).numpy())
+    torch.manual_seed(99)
+    dirs = ref_utils.generate_normalized_random_direction(5, 0.001, 0.1).numpy()
+    np.savez(os.path.join(HERE, "directions.npz"), seed99_count5=dirs)
+
+    # 2. render() under the two fixed scenes the reference's scripts/notebooks use -------
+    f32 = lambda *v: [float(np.float32(x)) for x in v]  # noqa: E731  (fp32-representable)
+    fixed = np.array([f32(0, -1, 2) + f32(0, 0, 2) + f32(50, 50, 50),          # renderers.py:284
+                      f32(0, -1, 1.4) + f32(1, 1, 1.7) + f32(30, 30, 30)],      # final-viz.ipynb cell 11
+                     dtype=np.float32)
+    maps = synthetic_maps(2, 24, 1001)
+    out = {"maps": maps.numpy(), "configs": fixed}
+    for name, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        torch.set_default_dtype(dtype)
+        renderer = ref_renderers.LocalRenderer()
+        scenes = scenes_from_configs(ref_env, torch.from_numpy(fixed))
+        out["render4d_" + name] = torch.stack([renderer.render(s, maps.to(dtype)) for s in scenes]).numpy()  # [2,B,3,H,W]
+        out["render3d_" + name] = renderer.render(scenes[0], maps[0].to(dtype)).numpy()                       # [1,3,H,W]
+        torch.set_default_dtype(torch.float32)
+    np.savez(os.path.join(HERE, "render_fixed.npz"), **out)
+
+    # 3. RenderingLoss fwd+bwd, bench distribution and stress distribution ---------------
+    for tag, size, stress, seed_in, seed_tg in (("bench", 24, False, 1002, 2002), ("stress", 16, True, 1003, 2003)):
+        inp, tgt = synthetic_maps(2, size, seed_in, stress), synthetic_maps(2, size, seed_tg, stress)
+        cfg = sample_configs(ref_env, 313, 2, 3, 6)
+        out = {"input": inp.numpy(), "target": tgt.numpy(), "configs": cfg.numpy()}
+        for name, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+            loss, grad, renders = reference_loss(ref, dtype, inp, tgt, cfg, 3)
+            out["loss_" + name], out["grad_" + name], out["renders_" + name] = loss, grad, renders
+        np.savez(os.path.join(HERE, "loss_%s.npz" % tag), **out)
+
+    # 4. N != 9 (27 configs = 9 random + 18 specular), tiny maps ------------------------
+    inp, tgt = synthetic_maps(1, 8, 1004), synthetic_maps(1, 8, 2004)
+    cfg = sample_configs(ref_env, 7, 1, 9, 18)
+    out = {"input": inp.numpy(), "target": tgt.numpy(), "configs": cfg.numpy()}
+    for name, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        loss, grad, _ = reference_loss(ref, dtype, inp, tgt, cfg, 9)
+        out["loss_" + name], out["grad_" + name] = loss, grad
+    np.savez(os.path.join(HERE, "loss_n27.npz"), **out)
+
+    # 5. MixedLoss value (losses.py:54-63) on the bench fixture, sampled scenes -----------
+    inp, tgt = synthetic_maps(2, 24, 1002), synthetic_maps(2, 24, 2002)
+    cfg = sample_configs(ref_env, 313, 2, 3, 6)
+    torch.manual_seed(313)
+    mixed = ref_losses.MixedLoss(ref_renderers.LocalRenderer())
+    x = inp.clone().requires_grad_(True)
+    val = mixed(x, tgt)
+    val.backward()
+    l1 = ref_losses.SVBRDFL1Loss()(inp, tgt)
+    np.savez(os.path.join(HERE, "mixed.npz"), loss_f32=val.detach().numpy(), grad_f32=x.grad.numpy(),
+             l1_f32=l1.numpy(), seed=np.int64(313))
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print("%-20s %8.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))
+
+
+if __name__ == "__main__":
+    main()
