@@ -1,0 +1,143 @@
+/*
+ * svbrdf_b200.h - C ABI of the B200-native rendering-loss path.
+ *
+ * Drop-in boundary for the one hot path of mworchel/svbrdf-estimation that this library
+ * replaces (paths relative to development/multiImage_pytorch/ of the reference):
+ *
+ *   LocalRenderer.render(scene, svbrdf)         renderers.py:67-104
+ *   RenderingLoss.forward(input, target)        losses.py:29-52
+ *   MixedLoss / SVBRDFL1Loss                    losses.py:7-19, 54-63   (caller of the path)
+ *   Camera / Light / Scene                      environment.py:4-16     (the "scene record")
+ *
+ * The reference has no FFI of its own (it is eager PyTorch); the host side that binds
+ * these symbols is svbrdf_estimation_b200/_cabi.py (ctypes), and INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All "dev" pointers are device memory of the CURRENT
+ *     CUDA device, fp32, contiguous NCHW; "host" pointers are ordinary host memory.
+ *   - The caller owns every buffer.  The library allocates nothing in the device-pointer
+ *     entry points, keeps no state between calls, and is re-entrant.  (The *_host entry
+ *     points use an explicit context object that owns staging buffers and streams.)
+ *   - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream).  Nothing synchronises unless documented.
+ *   - Return value: 0 on success, otherwise a negative SVBRDF_E_* code or a positive
+ *     cudaError_t; svbrdf_b200_last_error() gives a thread-local message.  Nothing throws.
+ *   - Maps are [B,12,H,W] with channels 0-2 normals, 3-5 diffuse, 6-8 roughness (one per
+ *     colour channel), 9-11 specular (utils.py:36-58).  H must equal W (renderers.py:73-76).
+ *   - A scene record is 9 floats: camera xyz, light xyz, light colour rgb.  Scene records
+ *     are HOST memory: they travel to the device as kernel parameters (constant bank),
+ *     so there is no scene upload and no device-side scene buffer.
+ *   - `lin` is the W-entry coordinate table torch.linspace(-1, 1, W) (renderers.py:73);
+ *     pixel (row, col) sits at (lin[col], -lin[row], 0).
+ */
+#ifndef SVBRDF_B200_H
+#define SVBRDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVBRDF_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SVBRDF_API __attribute__((visibility("default")))
+#else
+#define SVBRDF_API
+#endif
+
+#define SVBRDF_E_INVALID   (-1) /* bad argument (null pointer, non-positive size, H != W ...) */
+#define SVBRDF_E_TOO_LARGE (-2) /* size exceeds what the index arithmetic supports            */
+#define SVBRDF_E_STATE     (-3) /* context misuse in the *_host entry points                  */
+
+SVBRDF_API int svbrdf_b200_abi_version(void);
+
+/* Thread-local description of the last non-zero status returned on this thread. */
+SVBRDF_API const char* svbrdf_b200_last_error(void);
+
+/* Bytes of device workspace the loss entry points need for a [B,12,H,W] problem with N
+ * scene records per batch element (per-CTA loss partials).  Never 0.                      */
+SVBRDF_API size_t svbrdf_b200_workspace_bytes(int B, int N, int H, int W);
+
+/* ---- LocalRenderer.render (renderers.py:67-104) ------------------------------------------
+ * images[b,k,:,:,:] = radiance of maps[b] under scene record k of batch element b.
+ *   scenes_host : [B,N,9] if scenes_per_batch != 0, else [N,9] shared by every b
+ *                 (render(scene, svbrdf) applies ONE scene to the whole batch).
+ *   images_dev  : [B,N,3,H,W], linear radiance, unclamped.                                   */
+SVBRDF_API int svbrdf_b200_render_forward(const float* maps_dev, int B, int H, int W,
+                               const float* scenes_host, int N, int scenes_per_batch,
+                               const float* lin_dev, float* images_dev, void* stream);
+
+/* Vector-Jacobian product of the above w.r.t. the maps (autograd of renderers.py:67-104):
+ * grad_maps[b,:,:,:] = sum_k J^T grad_images[b,k].  grad_maps_dev is overwritten.          */
+SVBRDF_API int svbrdf_b200_render_backward(const float* maps_dev, int B, int H, int W,
+                                const float* scenes_host, int N, int scenes_per_batch,
+                                const float* lin_dev, const float* grad_images_dev,
+                                float* grad_maps_dev, void* stream);
+
+/* ---- RenderingLoss.forward (losses.py:29-52) ------------------------------------------------
+ * loss = mean_{b,k,c,y,x} | log(R(input)+0.1) - log(R(target)+0.1) |, written as one float
+ * to loss_dev.  scenes_host is [B,N,9] (fresh scenes per batch element, losses.py:35).
+ * Deterministic: per-CTA partials are summed in a fixed order in fp64.                       */
+SVBRDF_API int svbrdf_b200_loss_forward(const float* input_dev, const float* target_dev, int B, int H, int W,
+                             const float* scenes_host, int N, const float* lin_dev,
+                             float* loss_dev, void* workspace_dev, size_t workspace_bytes,
+                             void* stream);
+
+/* Same pass that also writes grad_input_dev[B,12,H,W] = d loss / d input (the target never
+ * requires grad in the reference's callers, main.py:111,116).  The gradient is for an
+ * upstream gradient of 1; see svbrdf_b200_scale_grad.                                        */
+SVBRDF_API int svbrdf_b200_loss_forward_backward(const float* input_dev, const float* target_dev,
+                                      int B, int H, int W, const float* scenes_host, int N,
+                                      const float* lin_dev, float* loss_dev, float* grad_input_dev,
+                                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* grad[i] *= *upstream_dev for i < count, in place; returns immediately on the device when
+ * *upstream_dev == 1.0f (the loss.backward() case), so no host synchronisation is needed
+ * to skip the pass.                                                                          */
+SVBRDF_API int svbrdf_b200_scale_grad(float* grad_dev, size_t count, const float* upstream_dev, void* stream);
+
+/* ---- MixedLoss (losses.py:54-63): l1_weight * SVBRDFL1Loss + RenderingLoss in one pass ------
+ * out_dev[0] = mixed loss, out_dev[1] = rendering loss, out_dev[2] = map L1 loss (unweighted).
+ * grad_input_dev may be NULL (forward only).                                                 */
+SVBRDF_API int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, const float* target_dev,
+                                            int B, int H, int W, const float* scenes_host, int N,
+                                            float l1_weight, const float* lin_dev, float* out_dev,
+                                            float* grad_input_dev, void* workspace_dev,
+                                            size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer entry point (the call a non-PyTorch caller makes) --------------------------
+ * A context owns pinned staging buffers, device buffers and copy/compute streams for problems
+ * up to the given size on the current device.                                                */
+typedef struct svbrdf_b200_ctx svbrdf_b200_ctx;
+
+SVBRDF_API int svbrdf_b200_ctx_create(svbrdf_b200_ctx** out, int max_B, int max_N, int H, int W);
+SVBRDF_API void svbrdf_b200_ctx_destroy(svbrdf_b200_ctx* ctx);
+
+/* Pinned host buffers owned by the context (input, target, grad: max_B*12*H*W floats each).
+ * Filling these directly avoids an extra host-side copy.  which: 0 input, 1 target, 2 grad.  */
+SVBRDF_API float* svbrdf_b200_ctx_pinned(svbrdf_b200_ctx* ctx, int which);
+
+/* RenderingLoss forward+backward on HOST maps: uploads input/target (batch-chunked, copies
+ * overlapped with the kernels), computes, downloads grad_input and the loss.  input_host /
+ * target_host / grad_host may be the context's pinned buffers or any host memory (pageable
+ * memory is staged through the pinned buffers).  Blocks until the results are on the host.  */
+SVBRDF_API int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* ctx, const float* input_host,
+                                    const float* target_host, int B, const float* scenes_host,
+                                    int N, float* loss_host, float* grad_host);
+
+/* ---- measurement helpers (bench.py only) -------------------------------------------------------
+ * Register-resident FP32 throughput probes used as measured roofline denominators.
+ * kind: 0 = dependent-chain-free FFMA, 1 = packed fma.rn.f32x2, 2 = MUFU.RCP, 3 = FMUL+FADD mix.
+ * Launches `blocks` CTAs of 256 threads running `iters` unrolled groups; *ops_per_thread_iter
+ * receives the number of counted operations (FMA = 1 op) per thread per iteration.          */
+SVBRDF_API int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* sink_dev,
+                             int* ops_per_thread_iter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVBRDF_B200_H */

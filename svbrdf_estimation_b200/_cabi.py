@@ -1,0 +1,87 @@
+"""ctypes binding of ``libsvbrdf_b200.so`` (C ABI declared in ``include/svbrdf_b200.h``).
+
+There is deliberately no fallback: if the shared library cannot be loaded the import of any
+product entry point raises, and every non-zero status from the library becomes an exception.
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsvbrdf_b200.so")
+
+E_INVALID, E_TOO_LARGE, E_STATE = -1, -2, -3
+
+_c_float_p = ctypes.c_void_p   # raw addresses (tensor.data_ptr()) are passed as integers
+_c_stream = ctypes.c_void_p
+
+# name -> (restype, argtypes); kept in the order of include/svbrdf_b200.h
+PROTOTYPES = {
+    "svbrdf_b200_abi_version": (ctypes.c_int, []),
+    "svbrdf_b200_last_error": (ctypes.c_char_p, []),
+    "svbrdf_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "svbrdf_b200_render_forward": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                  ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_stream]),
+    "svbrdf_b200_render_backward": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                   ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p,
+                                                   _c_stream]),
+    "svbrdf_b200_loss_forward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                                ctypes.c_size_t, _c_stream]),
+    "svbrdf_b200_loss_forward_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
+                                                         _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                         _c_stream]),
+    "svbrdf_b200_scale_grad": (ctypes.c_int, [_c_float_p, ctypes.c_size_t, _c_float_p, _c_stream]),
+    "svbrdf_b200_mixed_loss_forward_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                               ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float,
+                                                               _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                                               ctypes.c_size_t, _c_stream]),
+    "svbrdf_b200_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int]),
+    "svbrdf_b200_ctx_destroy": (None, [ctypes.c_void_p]),
+    "svbrdf_b200_ctx_pinned": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "svbrdf_b200_rendering_loss_host": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                                       _c_float_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                                       _c_float_p]),
+    "svbrdf_b200_probe_launch": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                ctypes.POINTER(ctypes.c_int), _c_stream]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SvbrdfB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, status, message):
+        super().__init__("svbrdf_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+def lib():
+    """The loaded library (built on first use if the in-tree .so is missing and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import _build
+            _build.build()          # raises if nvcc is unavailable: no silent fallback
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(handle, name)   # AttributeError if the .so does not export the header's symbol
+            fn.restype, fn.argtypes = restype, argtypes
+        if handle.svbrdf_b200_abi_version() != 1:
+            raise RuntimeError("libsvbrdf_b200.so has ABI version %d, expected 1" % handle.svbrdf_b200_abi_version())
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().svbrdf_b200_last_error()
+        raise SvbrdfB200Error(status, msg.decode("utf-8", "replace") if msg else "")

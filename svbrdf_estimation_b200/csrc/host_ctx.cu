@@ -1,0 +1,165 @@
+// host_ctx.cu - host-buffer entry point of the rendering-loss path.
+//
+// svbrdf_b200_rendering_loss_host() is the call a caller without device memory makes: maps live
+// in host memory, the loss and d loss / d input come back to host memory.  It is what bench.py
+// times as "e2e".  The batch is cut into slices; slice i's upload (H2D stream), its kernel
+// (compute stream) and the download of its gradient (D2H stream) overlap with the neighbouring
+// slices', so the PCIe link - not the kernel - is the bound and both directions are busy at once.
+//
+// Reference call being replaced: RenderingLoss.forward + loss.backward()
+// (development/multiImage_pytorch/losses.py:29-52, main.py:116-117) on CPU-resident tensors.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/svbrdf_b200.h"
+#include "internal.h"
+
+struct svbrdf_b200_ctx {
+    int max_B, max_N, H, W, device;
+    size_t map_floats;                       // 12*H*W
+    float *d_in, *d_tg, *d_gr, *d_lin, *d_loss, *d_ws;
+    float *h_in, *h_tg, *h_gr, *h_loss;      // pinned
+    size_t ws_bytes;
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t* ev_up;                      // per slice: upload done
+    cudaEvent_t* ev_k;                       // per slice: kernel done
+    int max_slices;
+};
+
+// torch.linspace(-1, 1, W) in fp32: step = (end-start)/(W-1); the first half counts up from the
+// start, the second half counts down from the end (ATen RangeFactories), which makes the table
+// antisymmetric.  renderers.py:73.
+static void fill_lin(float* lin, int W) {
+    if (W == 1) { lin[0] = -1.f; return; }
+    const float start = -1.f, end = 1.f;
+    const float step = (end - start) / (float)(W - 1);
+    const int half = W / 2;
+    for (int i = 0; i < W; ++i) {
+        volatile float prod = (i < half) ? step * (float)i : step * (float)(W - 1 - i);   // no FMA contraction
+        lin[i] = (i < half) ? start + prod : end - prod;
+    }
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) { rc = svb_cuda_status(e_, #call); goto done; } \
+    } while (0)
+
+extern "C" void svbrdf_b200_ctx_destroy(svbrdf_b200_ctx* c) {
+    if (!c) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    if (c->ev_up) for (int i = 0; i < c->max_slices; ++i) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+    if (c->ev_k) for (int i = 0; i < c->max_slices; ++i) if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+    free(c->ev_up); free(c->ev_k);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    cudaFree(c->d_in); cudaFree(c->d_tg); cudaFree(c->d_gr); cudaFree(c->d_lin); cudaFree(c->d_loss); cudaFree(c->d_ws);
+    cudaFreeHost(c->h_in); cudaFreeHost(c->h_tg); cudaFreeHost(c->h_gr); cudaFreeHost(c->h_loss);
+    free(c);
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+extern "C" int svbrdf_b200_ctx_create(svbrdf_b200_ctx** out, int max_B, int max_N, int H, int W) {
+    if (!out) return svb_fail(SVBRDF_E_INVALID, "out is null");
+    *out = nullptr;
+    if (int e = svb_check_shape(max_B, H, W, max_N)) return e;
+    int rc = 0;
+    svbrdf_b200_ctx* c = (svbrdf_b200_ctx*)calloc(1, sizeof(svbrdf_b200_ctx));
+    if (!c) return svb_fail(SVBRDF_E_INVALID, "out of host memory");
+    float* lin = nullptr;
+    c->max_B = max_B; c->max_N = max_N; c->H = H; c->W = W;
+    c->map_floats = (size_t)12 * H * W;
+    c->max_slices = max_B < 16 ? max_B : 16;
+    {
+        const size_t bytes = (size_t)max_B * c->map_floats * sizeof(float);
+        CK(cudaGetDevice(&c->device));
+        CK(cudaMalloc(&c->d_in, bytes));
+        CK(cudaMalloc(&c->d_tg, bytes));
+        CK(cudaMalloc(&c->d_gr, bytes));
+        CK(cudaMalloc(&c->d_lin, (size_t)W * sizeof(float)));
+        CK(cudaMalloc(&c->d_loss, 4 * sizeof(float)));
+        c->ws_bytes = svbrdf_b200_workspace_bytes(max_B, max_N, H, W);
+        CK(cudaMalloc(&c->d_ws, c->ws_bytes));
+        CK(cudaMallocHost(&c->h_in, bytes));
+        CK(cudaMallocHost(&c->h_tg, bytes));
+        CK(cudaMallocHost(&c->h_gr, bytes));
+        CK(cudaMallocHost(&c->h_loss, 4 * sizeof(float)));
+        CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        c->ev_up = (cudaEvent_t*)calloc(c->max_slices, sizeof(cudaEvent_t));
+        c->ev_k = (cudaEvent_t*)calloc(c->max_slices, sizeof(cudaEvent_t));
+        if (!c->ev_up || !c->ev_k) { rc = svb_fail(SVBRDF_E_INVALID, "out of host memory"); goto done; }
+        for (int i = 0; i < c->max_slices; ++i) {
+            CK(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        }
+        lin = (float*)malloc((size_t)W * sizeof(float));
+        if (!lin) { rc = svb_fail(SVBRDF_E_INVALID, "out of host memory"); goto done; }
+        fill_lin(lin, W);
+        CK(cudaMemcpy(c->d_lin, lin, (size_t)W * sizeof(float), cudaMemcpyHostToDevice));
+    }
+done:
+    free(lin);
+    if (rc) { svbrdf_b200_ctx_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" float* svbrdf_b200_ctx_pinned(svbrdf_b200_ctx* c, int which) {
+    if (!c) return nullptr;
+    return which == 0 ? c->h_in : which == 1 ? c->h_tg : which == 2 ? c->h_gr : nullptr;
+}
+
+extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* input_host, const float* target_host,
+                                               int B, const float* scenes_host, int N, float* loss_host,
+                                               float* grad_host) {
+    if (!c) return svb_fail(SVBRDF_E_STATE, "context is null");
+    if (!input_host || !target_host || !scenes_host || !loss_host)
+        return svb_fail(SVBRDF_E_INVALID, "null pointer argument");
+    if (B <= 0 || B > c->max_B || N <= 0 || N > c->max_N)
+        return svb_fail(SVBRDF_E_INVALID, "B or N exceeds what the context was created for");
+    int rc = 0, prev = -1;
+    cudaGetDevice(&prev);
+    const int HW = c->H * c->W;
+    const int cpi = (HW + 255) / 256;
+    float* part_render = c->d_ws;
+    float* part_l1 = c->d_ws + (size_t)B * cpi;
+    // slices: enough to overlap the two copy directions with compute, not so many that launch
+    // overhead shows; every slice is at least one batch element.
+    const int slices = B < c->max_slices ? B : c->max_slices;
+    {
+        CK(cudaSetDevice(c->device));
+        for (int i = 0; i < slices; ++i) {
+            const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
+            const size_t off = (size_t)b0 * c->map_floats, cnt = (size_t)(b1 - b0) * c->map_floats;
+            CK(cudaMemcpyAsync(c->d_in + off, input_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaMemcpyAsync(c->d_tg + off, target_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaEventRecord(c->ev_up[i], c->s_h2d));
+            CK(cudaStreamWaitEvent(c->s_comp, c->ev_up[i], 0));
+            rc = svb_launch_loss_range(c->d_in, c->d_tg, grad_host ? c->d_gr : nullptr, B, HW, c->W, scenes_host, N,
+                                       c->d_lin, part_render, part_l1, false, 0.f, b0, b1 - b0, c->s_comp);
+            if (rc) goto done;
+            if (grad_host) {
+                CK(cudaEventRecord(c->ev_k[i], c->s_comp));
+                CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[i], 0));
+                CK(cudaMemcpyAsync(grad_host + off, c->d_gr + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+            }
+        }
+        rc = svb_launch_finalize(part_render, part_l1, B, HW, N, false, 0.f, c->d_loss, 1, c->s_comp);
+        if (rc) goto done;
+        CK(cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
+        CK(cudaStreamSynchronize(c->s_comp));
+        CK(cudaStreamSynchronize(c->s_d2h));
+        *loss_host = c->h_loss[0];
+    }
+done:
+    if (rc) { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}

@@ -1,0 +1,168 @@
+"""Scene records and the light/view configuration samplers of the rendering loss.
+
+Drop-in for the reference's ``environment.py`` (development/multiImage_pytorch/environment.py:4-55):
+``Camera``/``Light``/``Scene`` holders and ``generate_random_scenes`` / ``generate_specular_scenes``
+consume the global CPU generator in the reference's order, so ``torch.manual_seed(s)`` yields the
+same scenes as the reference does.  The CUDA path consumes scenes as packed float32 records
+``[.., 9] = (camera xyz, light xyz, light rgb)``; ``sample_loss_configs`` produces a whole
+``[B, N, 9]`` block for one loss evaluation without building Python objects.
+"""
+import numpy as np
+import torch
+
+from .utils import generate_normalized_random_direction, hemisphere_uniforms_to_directions
+
+RANDOM_LIGHT_COLOR = 20.0     # environment.py:27
+SPECULAR_LIGHT_COLOR = 50.0   # environment.py:52
+VIEW_EPS = (0.001, 0.1)       # environment.py:20-21,34
+LOG_DISTANCE = (0.5, 0.75)    # environment.py:38-39
+
+
+class Camera:
+    """Pinhole camera looking at the patch centre; only the position matters (environment.py:4-6)."""
+    __slots__ = ("pos",)
+
+    def __init__(self, pos):
+        self.pos = pos
+
+    def __repr__(self):
+        return "Camera(pos=%s)" % (_triple(self.pos),)
+
+
+class Light:
+    """Point light with RGB intensity (environment.py:8-11)."""
+    __slots__ = ("pos", "color")
+
+    def __init__(self, pos, color):
+        self.pos, self.color = pos, color
+
+    def __repr__(self):
+        return "Light(pos=%s, color=%s)" % (_triple(self.pos), _triple(self.color))
+
+
+class Scene:
+    """One light/view configuration (environment.py:13-16)."""
+    __slots__ = ("camera", "light")
+
+    def __init__(self, camera, light):
+        self.camera, self.light = camera, light
+
+    def __repr__(self):
+        return "Scene(%r, %r)" % (self.camera, self.light)
+
+
+def _triple(v):
+    """list / tuple / ndarray / tensor of 3 numbers -> list of 3 python floats rounded to fp32
+    (the reference converts with ``torch.Tensor(v)``, i.e. to fp32: renderers.py:79,91,98)."""
+    if isinstance(v, torch.Tensor):
+        a = v.detach().to(device="cpu", dtype=torch.float32).reshape(-1).numpy()
+    else:
+        a = np.asarray(v, dtype=np.float32).reshape(-1)
+    if a.shape[0] != 3:
+        raise ValueError("expected 3 components, got %d" % a.shape[0])
+    return [float(a[0]), float(a[1]), float(a[2])]
+
+
+def scene_record(scene):
+    """Scene -> [9] float32 CPU tensor (camera xyz, light xyz, light rgb)."""
+    return torch.tensor(_triple(scene.camera.pos) + _triple(scene.light.pos) + _triple(scene.light.color),
+                        dtype=torch.float32)
+
+
+def pack_scenes(scenes):
+    """Iterable of Scene -> [N,9] float32 CPU tensor."""
+    return torch.stack([scene_record(s) for s in scenes], dim=0)
+
+
+def unpack_scenes(records):
+    """[N,9] tensor -> list of Scene objects holding fp32 CPU tensors (like the reference's samplers)."""
+    records = torch.as_tensor(records, dtype=torch.float32).reshape(-1, 9)
+    return [Scene(Camera(r[0:3].clone()), Light(r[3:6].clone(), r[6:9].tolist())) for r in records]
+
+
+# ---- raw draws in the reference's order ------------------------------------------------------
+
+def _draw_random(view_u, light_u):
+    """Fills [count,2] buffers with (r1, r2) for the view and then the light directions
+    (environment.py:20-21 -> utils.py:101-102: all r1 first, then all r2)."""
+    lo, hi = 0.0 + VIEW_EPS[0], 1.0 - VIEW_EPS[1]
+    view_u[0].uniform_(lo, hi); view_u[1].uniform_(0.0, 1.0)
+    light_u[0].uniform_(lo, hi); light_u[1].uniform_(0.0, 1.0)
+
+
+def _draw_specular(view_u, log_dist, shift):
+    """(r1, r2) of the view direction, log-distances of view and light, xy shift
+    (environment.py:34,38-39,44)."""
+    view_u[0].uniform_(0.0 + VIEW_EPS[0], 1.0 - VIEW_EPS[1]); view_u[1].uniform_(0.0, 1.0)
+    log_dist[0].normal_(mean=LOG_DISTANCE[0], std=LOG_DISTANCE[1])
+    log_dist[1].normal_(mean=LOG_DISTANCE[0], std=LOG_DISTANCE[1])
+    shift.uniform_(-1.0, 1.0)
+
+
+def _random_records(view_u, light_u):
+    """[...,2,count] uniforms -> [...,count,9] records: unit-distance camera and light, colour 20
+    (environment.py:18-30)."""
+    cam = hemisphere_uniforms_to_directions(view_u[..., 0, :], view_u[..., 1, :])
+    light = hemisphere_uniforms_to_directions(light_u[..., 0, :], light_u[..., 1, :])
+    return torch.cat((cam, light, torch.full_like(cam, RANDOM_LIGHT_COLOR)), dim=-1)
+
+
+def _specular_records(view_u, log_dist, shift):
+    """Mirror configurations (environment.py:32-55): light direction = view * (-1,-1,1), independent
+    log-normal distances, common xy shift with z = 1e-4, colour 50."""
+    view = hemisphere_uniforms_to_directions(view_u[..., 0, :], view_u[..., 1, :])
+    mirror = view * torch.tensor([-1.0, -1.0, 1.0])
+    dist = torch.exp(log_dist)
+    off = torch.cat((shift, torch.zeros_like(shift[..., :1]) + 0.0001), dim=-1)
+    cam = view * dist[..., 0, :, None] + off
+    light = mirror * dist[..., 1, :, None] + off
+    return torch.cat((cam, light, torch.full_like(cam, SPECULAR_LIGHT_COLOR)), dim=-1)
+
+
+def sample_loss_configs(batch, n_random=3, n_specular=6):
+    """Scene records of one ``RenderingLoss.forward`` call: for each batch element, ``n_random``
+    random then ``n_specular`` mirror configurations (losses.py:34-35) -> [batch, N, 9] float32 CPU.
+
+    The generator is consumed element by element in the reference's order (so a seed reproduces the
+    reference's scenes bit for bit); the trigonometry runs once over the whole block."""
+    ru_v = torch.empty(batch, 2, n_random); ru_l = torch.empty(batch, 2, n_random)
+    su_v = torch.empty(batch, 2, n_specular); s_ld = torch.empty(batch, 2, n_specular)
+    s_sh = torch.empty(batch, n_specular, 2)
+    for b in range(batch):
+        _draw_random(ru_v[b], ru_l[b])
+        _draw_specular(su_v[b], s_ld[b], s_sh[b])
+    return torch.cat((_random_records(ru_v, ru_l), _specular_records(su_v, s_ld, s_sh)), dim=1).contiguous()
+
+
+def sample_loss_configs_fast(batch, n_random=3, n_specular=6, generator=None):
+    """Same distributions as :func:`sample_loss_configs` with one generator call per quantity for
+    the whole batch (not draw-order compatible with the reference)."""
+    def uni(shape, lo, hi):
+        return torch.empty(shape).uniform_(lo, hi, generator=generator)
+    lo, hi = VIEW_EPS[0], 1.0 - VIEW_EPS[1]
+    def dirs_u(n):
+        return torch.stack((uni((batch, n), lo, hi), uni((batch, n), 0.0, 1.0)), dim=1)
+    log_dist = torch.empty(batch, 2, n_specular).normal_(LOG_DISTANCE[0], LOG_DISTANCE[1], generator=generator)
+    shift = uni((batch, n_specular, 2), -1.0, 1.0)
+    return torch.cat((_random_records(dirs_u(n_random), dirs_u(n_random)),
+                      _specular_records(dirs_u(n_specular), log_dist, shift)), dim=1).contiguous()
+
+
+def generate_random_scenes(count):
+    """``count`` Scenes with independently cosine-sampled view and light directions used as
+    positions, light colour 20 (environment.py:18-30)."""
+    view_u, light_u = torch.empty(2, count), torch.empty(2, count)
+    _draw_random(view_u, light_u)
+    return unpack_scenes(_random_records(view_u, light_u))
+
+
+def generate_specular_scenes(count):
+    """``count`` Scenes in mirror configuration, light colour 50 (environment.py:32-55)."""
+    view_u, log_dist, shift = torch.empty(2, count), torch.empty(2, count), torch.empty(count, 2)
+    _draw_specular(view_u, log_dist, shift)
+    return unpack_scenes(_specular_records(view_u, log_dist, shift))
+
+
+__all__ = ["Camera", "Light", "Scene", "generate_random_scenes", "generate_specular_scenes",
+           "generate_normalized_random_direction", "pack_scenes", "unpack_scenes", "scene_record",
+           "sample_loss_configs", "sample_loss_configs_fast"]

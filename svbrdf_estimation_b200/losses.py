@@ -1,0 +1,188 @@
+"""Rendering loss and its callers behind the reference's ``nn.Module`` interface.
+
+Drop-in for ``losses.py`` of the reference (development/multiImage_pytorch/losses.py:7-63).
+With the B200 ``LocalRenderer`` plugged in, ``RenderingLoss`` runs ONE fused kernel that shades
+input and target maps under all sampled light/view configurations, reduces the log-L1 difference
+and writes d loss / d input in the same pass; ``MixedLoss`` folds the map-space L1 terms into that
+pass as well.  Any other renderer object (e.g. a path-tracer wrapper with the same
+``render(scene, svbrdf)`` method) goes through the generic per-scene loop of the plugin API.
+"""
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from . import environment as env
+from .renderers import as_device_maps, as_host_records, coordinate_table
+from .utils import unpack_svbrdf
+
+EPSILON_RENDER = 0.1   # losses.py:46
+EPSILON_L1 = 0.01      # losses.py:13
+
+
+def _workspace(B, N, H, W, device):
+    nbytes = _cabi.lib().svbrdf_b200_workspace_bytes(B, N, H, W)
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32), nbytes
+
+
+def _check_pair(input, target):
+    if input.shape != target.shape:
+        raise ValueError("input and target shapes differ: %s vs %s" % (tuple(input.shape), tuple(target.shape)))
+    if input.dim() != 4:
+        raise ValueError("expected [B,12,H,W] tensors, got %s" % (tuple(input.shape),))
+    if input.device != target.device:
+        raise ValueError("input and target are on different devices")
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss (and d loss/d input computed in the same kernel pass) for given host scene records.
+
+    ``l1_weight is None`` -> RenderingLoss; otherwise MixedLoss with that weight, and the returned
+    tensor has 3 entries (mixed, rendering, map-L1)."""
+
+    @staticmethod
+    def forward(ctx, input, target, records, l1_weight):
+        B, _, H, W = input.shape
+        N = records.shape[1]
+        lib = _cabi.lib()
+        mixed = l1_weight is not None
+        out = torch.empty(3 if mixed else 1, device=input.device, dtype=torch.float32)
+        ws, ws_bytes = _workspace(B, N, H, W, input.device)
+        lin = coordinate_table(W, input.device)
+        want_in, want_tg = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_in = torch.empty_like(input) if want_in else None
+        with torch.cuda.device(input.device):
+            stream = torch.cuda.current_stream().cuda_stream
+
+            def run(a, b, g):
+                gp = g.data_ptr() if g is not None else None
+                if mixed:
+                    _cabi.check(lib.svbrdf_b200_mixed_loss_forward_backward(
+                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight),
+                        lin.data_ptr(), out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream))
+                elif g is not None:
+                    _cabi.check(lib.svbrdf_b200_loss_forward_backward(
+                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(),
+                        out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream))
+                else:
+                    _cabi.check(lib.svbrdf_b200_loss_forward(
+                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(),
+                        out.data_ptr(), ws.data_ptr(), ws_bytes, stream))
+
+            run(input, target, grad_in)
+            grad_tg = None
+            if want_tg:
+                # the loss is symmetric in its arguments: d/d target = the same kernel with the roles swapped
+                grad_tg = torch.empty_like(target)
+                scratch = torch.empty_like(out)
+                keep, out = out, scratch
+                run(target, input, grad_tg)
+                out = keep
+        ctx.grads = (grad_in, grad_tg)
+        ctx.mixed = mixed
+        return out if mixed else out.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.grads is None:
+            raise RuntimeError("the fused rendering loss was already back-propagated; its gradient buffer "
+                               "is handed to autograd on the first backward()")
+        grad_in, grad_tg = ctx.grads
+        ctx.grads = None
+        up = grad_out.reshape(-1)[0:1].to(torch.float32).contiguous()   # d/d(mixed or rendering loss)
+        if ctx.mixed and bool((grad_out.reshape(-1)[1:] != 0).any()):
+            raise NotImplementedError("only the first entry (the mixed loss) of the fused MixedLoss output "
+                                      "is differentiable")
+        lib = _cabi.lib()
+        for g in (grad_in, grad_tg):
+            if g is not None:
+                with torch.cuda.device(g.device):
+                    _cabi.check(lib.svbrdf_b200_scale_grad(g.data_ptr(), g.numel(), up.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream))
+        return grad_in, grad_tg, None, None
+
+
+def _fused_loss(input, target, records, l1_weight):
+    _check_pair(input, target)
+    a, _, origin = as_device_maps(input, "input")
+    b, _, _ = as_device_maps(target, "target")
+    rec = as_host_records(records, a.shape[0])
+    if rec.dim() != 3:
+        raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
+    out = _FusedLoss.apply(a, b, rec, l1_weight)
+    return out if origin.type == "cuda" else out.to(origin)
+
+
+def rendering_loss_with_records(input, target, records):
+    """``RenderingLoss`` for explicit scene records ``[B,N,9]`` (no sampling) - the notebook-style
+    fixed-scene loss and the form the parity tests use."""
+    return _fused_loss(input, target, records, None)
+
+
+class SVBRDFL1Loss(nn.Module):
+    """Sum of four mean-L1 terms over the map groups, diffuse and specular compared as
+    ``log(x + 0.01)`` (losses.py:7-19).  Stand-alone (unfused) form, plain torch ops on the
+    tensors' device; ``MixedLoss`` fuses it into the rendering-loss kernel."""
+
+    def forward(self, input, target):
+        n0, d0, r0, s0 = unpack_svbrdf(input)
+        n1, d1, r1, s1 = unpack_svbrdf(target)
+        l1 = nn.functional.l1_loss
+        return (l1(n0, n1) + l1(torch.log(d0 + EPSILON_L1), torch.log(d1 + EPSILON_L1))
+                + l1(r0, r1) + l1(torch.log(s0 + EPSILON_L1), torch.log(s1 + EPSILON_L1)))
+
+
+class RenderingLoss(nn.Module):
+    """mean | log(render(input)+0.1) - log(render(target)+0.1) | under freshly sampled light/view
+    configurations per batch element (losses.py:21-52).  No parameters, no buffers."""
+
+    def __init__(self, renderer):
+        super().__init__()
+        self.renderer = renderer
+        self.random_configuration_count = 3     # losses.py:26
+        self.specular_configuration_count = 6   # losses.py:27
+
+    def sample_records(self, batch_size):
+        """[B,N,9] scene records drawn from the global CPU generator in the reference's order."""
+        return env.sample_loss_configs(batch_size, self.random_configuration_count,
+                                       self.specular_configuration_count)
+
+    def forward(self, input, target):
+        if getattr(self.renderer, "fused_rendering_loss", False):
+            _check_pair(input, target)
+            return _fused_loss(input, target, self.sample_records(input.shape[0]), None)
+        return self._forward_with_plugin(input, target)
+
+    def _forward_with_plugin(self, input, target):
+        """Generic renderer plugin: one ``render`` call per (sample, scene, map) like losses.py:34-50."""
+        ins, tgs = [], []
+        for i in range(input.shape[0]):
+            scenes = (env.generate_random_scenes(self.random_configuration_count)
+                      + env.generate_specular_scenes(self.specular_configuration_count))
+            ins.append(torch.cat([self.renderer.render(s, input[i]) for s in scenes], dim=0))
+            tgs.append(torch.cat([self.renderer.render(s, target[i]) for s in scenes], dim=0))
+        a = torch.log(torch.stack(ins, dim=0) + EPSILON_RENDER)
+        b = torch.log(torch.stack(tgs, dim=0) + EPSILON_RENDER)
+        return nn.functional.l1_loss(a, b)
+
+
+class MixedLoss(nn.Module):
+    """``l1_weight * SVBRDFL1Loss + RenderingLoss`` (losses.py:54-63) - what the training script
+    builds (main.py:89).  With the fused renderer both terms and their gradient come from one
+    kernel pass over the maps."""
+
+    def __init__(self, renderer, l1_weight=0.1):
+        super().__init__()
+        self.l1_weight = l1_weight
+        self.l1_loss = SVBRDFL1Loss()
+        self.rendering_loss = RenderingLoss(renderer)
+
+    def forward(self, input, target):
+        rl = self.rendering_loss
+        if getattr(rl.renderer, "fused_rendering_loss", False):
+            _check_pair(input, target)
+            out = _fused_loss(input, target, rl.sample_records(input.shape[0]), float(self.l1_weight))
+            return out[0]
+        return self.l1_weight * self.l1_loss(input, target) + rl(input, target)
+
+
+__all__ = ["SVBRDFL1Loss", "RenderingLoss", "MixedLoss", "rendering_loss_with_records"]

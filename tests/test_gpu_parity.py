@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the reference-facing Python interface and the C ABI) with the
+oracle and the golden fixtures of the unmodified reference.  Needs a GPU: ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as O
+from tests import parity
+from tests.common import synthetic_maps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import svbrdf_estimation_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device"
+    return pkg
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ours_loss_and_grad(S, inp, tgt, cfg):
+    x = cu(inp).requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, cu(tgt), torch.from_numpy(cfg))
+    loss.backward()
+    return float(loss), x.grad.cpu().numpy()
+
+
+# ---- golden fixtures (outputs of the unmodified reference, fp32 and fp64) ------------------------
+
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27"])
+def test_loss_and_gradient_vs_reference(S, golden, fixture):
+    g = golden(fixture)
+    loss, grad = ours_loss_and_grad(S, g["input"], g["target"], g["configs"])
+    parity.check_loss(loss, g["loss_f64"])
+    parity.check_grad_groups(grad, g["grad_f32"], g["grad_f64"])
+
+
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress"])
+def test_renders_vs_reference(S, golden, fixture):
+    g = golden(fixture)
+    got = S.render_records(cu(g["input"]), torch.from_numpy(g["configs"])).cpu().numpy()
+    parity.check_tensor(got, g["renders_f32"], g["renders_f64"], "renders")
+    dlog = np.abs(np.log(got.astype(np.float64) + 0.1) - np.log(g["renders_f64"] + 0.1)).max()
+    assert dlog < 2e-3, dlog
+
+
+def test_render_interface_fixed_scenes(S, golden):
+    """LocalRenderer.render(scene, svbrdf): 4-D and 3-D inputs, list-valued scene fields
+    (renderers.py:284 and final-viz.ipynb cell 11 scenes)."""
+    g = golden("render_fixed")
+    maps = cu(g["maps"])
+    r = S.LocalRenderer()
+    for k, cfg in enumerate(g["configs"]):
+        scene = S.Scene(S.Camera(cfg[0:3].tolist()), S.Light(cfg[3:6].tolist(), cfg[6:9].tolist()))
+        out = r.render(scene, maps)
+        assert out.shape == (2, 3, 24, 24) and out.device == maps.device
+        parity.check_tensor(out.cpu().numpy(), g["render4d_f32"][k], g["render4d_f64"][k], "render4d[%d]" % k)
+    scene = S.Scene(S.Camera(g["configs"][0, 0:3]), S.Light(torch.from_numpy(g["configs"][0, 3:6]), g["configs"][0, 6:9]))
+    out3 = r.render(scene, maps[0])
+    assert out3.shape == (1, 3, 24, 24)
+    parity.check_tensor(out3.cpu().numpy(), g["render3d_f32"], g["render3d_f64"], "render3d")
+    out5 = r.render(scene, maps.reshape(1, 2, 12, 24, 24))
+    assert out5.shape == (1, 2, 3, 24, 24)
+    assert torch.equal(out5[0, 0:1], out3)
+
+
+def test_mixed_loss_vs_reference(S, golden):
+    g, gm = golden("loss_bench"), golden("mixed")
+    torch.manual_seed(int(gm["seed"]))
+    x = cu(g["input"]).requires_grad_(True)
+    val = S.MixedLoss(S.LocalRenderer())(x, cu(g["target"]))
+    val.backward()
+    assert val.dim() == 0
+    assert abs(float(val) - float(gm["loss_f32"])) <= 3e-6 * abs(float(gm["loss_f32"]))
+    o32 = gm["grad_f32"]
+    for name, s in parity.GROUPS:
+        e = parity.rel_l2(x.grad.cpu().numpy()[:, s], o32[:, s])
+        assert e <= 1.5e-4, (name, e)
+    # unfused SVBRDFL1Loss on the device
+    l1 = S.SVBRDFL1Loss()(cu(g["input"]), cu(g["target"]))
+    assert abs(float(l1) - float(gm["l1_f32"])) <= 1e-5 * float(gm["l1_f32"])
+
+
+# ---- seeded inputs at sizes the oracle finishes in seconds --------------------------------------
+
+@pytest.mark.parametrize("size,batch,stress", [(64, 3, False), (48, 2, True), (37, 2, False)])
+def test_loss_and_gradient_vs_oracle(S, size, batch, stress):
+    inp, tgt = synthetic_maps(batch, size, 11, stress), synthetic_maps(batch, size, 12, stress)
+    torch.manual_seed(313)
+    cfg = O.sample_loss_configs(batch)
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+    l32, g32 = O.rendering_loss_and_grad(inp, tgt, cfg)
+    loss, grad = ours_loss_and_grad(S, inp.numpy(), tgt.numpy(), cfg.numpy())
+    parity.check_loss(loss, float(l64))
+    parity.check_grad_groups(grad, g32.numpy(), g64.numpy())
+
+
+def test_rendering_loss_module_draws_reference_scenes(S):
+    """RenderingLoss(LocalRenderer())(input, target) after torch.manual_seed(s) evaluates the same
+    scenes as the reference (losses.py:35) -> equals the oracle with oracle-sampled scenes."""
+    inp, tgt = synthetic_maps(2, 32, 21), synthetic_maps(2, 32, 22)
+    torch.manual_seed(1234)
+    cfg = O.sample_loss_configs(2)
+    want = float(O.rendering_loss(inp.double(), tgt.double(), cfg))
+    mod = S.RenderingLoss(S.LocalRenderer())
+    torch.manual_seed(1234)
+    got = mod(inp.cuda(), tgt.cuda())
+    assert got.dim() == 0 and got.is_cuda
+    parity.check_loss(float(got), want)
+    # the two configuration counts are honoured at call time (losses.py:26-27)
+    mod.random_configuration_count, mod.specular_configuration_count = 9, 18
+    torch.manual_seed(77)
+    cfg27 = O.sample_loss_configs(2, 9, 18)
+    torch.manual_seed(77)
+    parity.check_loss(float(mod(inp.cuda(), tgt.cuda())), float(O.rendering_loss(inp.double(), tgt.double(), cfg27)))
+
+
+def test_render_backward_vs_oracle_autograd(S):
+    maps = synthetic_maps(2, 40, 31, stress=True)
+    torch.manual_seed(5)
+    cfg = O.sample_loss_configs(2)
+    w = torch.randn(2, 9, 3, 40, 40)
+    m64 = maps.double().requires_grad_(True)
+    (O.render_batch(m64, cfg) * w.double()).sum().backward()
+    m32 = maps.clone().requires_grad_(True)
+    (O.render_batch(m32, cfg) * w).sum().backward()
+    x = maps.cuda().requires_grad_(True)
+    (S.render_records(x, cfg) * w.cuda()).sum().backward()
+    parity.check_grad_groups(x.grad.cpu().numpy(), m32.grad.numpy(), m64.grad.numpy(), "render_bwd")
+
+
+def test_fixed_scene_loss_through_render_autograd(S):
+    """Notebook-style loss (website.ipynb cell 15): plain L1 between renders, autograd through render()."""
+    maps, tgt = synthetic_maps(1, 32, 41), synthetic_maps(1, 32, 42)
+    cfg = torch.tensor([[0.0, -1.0, 2.0, 0.0, 0.0, 2.0, 50.0, 50.0, 50.0]])
+    scene = S.Scene(S.Camera([0.0, -1.0, 2.0]), S.Light([0.0, 0.0, 2.0], [50.0, 50.0, 50.0]))
+    m64 = maps.double().requires_grad_(True)
+    ref = torch.nn.functional.l1_loss(O.render(cfg[0, 0:3], cfg[0, 3:6], cfg[0, 6:9], m64),
+                                      O.render(cfg[0, 0:3], cfg[0, 3:6], cfg[0, 6:9], tgt.double()))
+    ref.backward()
+    x = maps.cuda().requires_grad_(True)
+    r = S.LocalRenderer()
+    got = torch.nn.functional.l1_loss(r.render(scene, x), r.render(scene, tgt.cuda()))
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-5 * float(ref)
+    for name, s in parity.GROUPS:
+        assert parity.rel_l2(x.grad.cpu().numpy()[:, s], m64.grad.numpy()[:, s]) <= 2e-4, name
+
+
+# ---- interface behaviour ---------------------------------------------------------------------------
+
+def test_upstream_gradient_scaling_and_no_grad(S):
+    inp, tgt = synthetic_maps(2, 16, 51).cuda(), synthetic_maps(2, 16, 52).cuda()
+    cfg = O.sample_loss_configs(2)
+    x1 = inp.clone().requires_grad_(True)
+    S.rendering_loss_with_records(x1, tgt, cfg).backward()
+    x2 = inp.clone().requires_grad_(True)
+    (S.rendering_loss_with_records(x2, tgt, cfg) * 2.5).backward()
+    torch.testing.assert_close(x2.grad, x1.grad * 2.5, rtol=1e-6, atol=0)
+    with torch.no_grad():
+        v = S.rendering_loss_with_records(inp, tgt, cfg)
+    assert not v.requires_grad
+    assert float(v) == float(S.rendering_loss_with_records(x1.detach(), tgt, cfg))
+    # gradient w.r.t. the target (symmetric loss)
+    t = tgt.clone().requires_grad_(True)
+    S.rendering_loss_with_records(inp, t, cfg).backward()
+    x3 = tgt.clone().requires_grad_(True)
+    S.rendering_loss_with_records(x3, inp, cfg).backward()
+    torch.testing.assert_close(t.grad, x3.grad, rtol=0, atol=0)
+
+
+def test_identical_maps_zero_loss_zero_grad(S):
+    inp = synthetic_maps(2, 32, 61).cuda().requires_grad_(True)
+    loss = S.rendering_loss_with_records(inp, inp.detach().clone(), O.sample_loss_configs(2))
+    loss.backward()
+    assert float(loss) == 0.0 and not bool(inp.grad.any())
+
+
+def test_host_tensors_are_staged_through_the_gpu(S):
+    maps = synthetic_maps(1, 16, 71)
+    scene = S.Scene(S.Camera([0.0, -1.0, 2.0]), S.Light([0.0, 0.0, 2.0], torch.tensor([50.0, 50.0, 50.0])))
+    out = S.LocalRenderer().render(scene, maps)          # dataset.py:206-212 calls it like this
+    assert out.device.type == "cpu" and out.shape == (1, 3, 16, 16)
+    torch.testing.assert_close(out, S.LocalRenderer().render(scene, maps.cuda()).cpu(), rtol=0, atol=0)
+
+
+def test_argument_errors(S):
+    r = S.LocalRenderer()
+    scene = S.Scene(S.Camera([0, 0, 1]), S.Light([0, 0, 1], [1, 1, 1]))
+    with pytest.raises(ValueError):
+        r.render(scene, torch.zeros(12, 8, 6).cuda())          # non-square (renderers.py:73-76)
+    with pytest.raises(ValueError):
+        r.render(scene, torch.zeros(11, 8, 8).cuda())
+    with pytest.raises(TypeError):
+        r.render(scene, torch.zeros(12, 8, 8, dtype=torch.float64).cuda())
+    with pytest.raises(ValueError):
+        S.rendering_loss_with_records(torch.zeros(2, 12, 8, 8).cuda(), torch.zeros(1, 12, 8, 8).cuda(), torch.zeros(2, 9, 9))
+    with pytest.raises(ValueError):
+        S.rendering_loss_with_records(torch.zeros(2, 12, 8, 8).cuda(), torch.zeros(2, 12, 8, 8).cuda(), torch.zeros(3, 9, 9))
+
+
+def test_plugin_renderer_falls_back_to_generic_loop(S):
+    """A renderer object without the fused marker goes through render() per scene (plugin API)."""
+    class Wrapped:
+        def __init__(self):
+            self.inner, self.calls = S.LocalRenderer(), 0
+
+        def render(self, scene, svbrdf):
+            self.calls += 1
+            return self.inner.render(scene, svbrdf)
+
+    inp, tgt = synthetic_maps(2, 16, 81).cuda(), synthetic_maps(2, 16, 82).cuda()
+    w = Wrapped()
+    torch.manual_seed(9)
+    a = S.RenderingLoss(w)(inp, tgt)
+    torch.manual_seed(9)
+    b = S.RenderingLoss(S.LocalRenderer())(inp, tgt)
+    assert w.calls == 2 * 2 * 9
+    assert abs(float(a) - float(b)) <= 2e-6 * float(b)
+
+
+def test_ragged_sizes_and_many_records(S):
+    """Odd map sizes (tail CTA), 1x1 maps, N that needs several launches (records > parameter block)."""
+    for size, batch, n in ((1, 1, 1), (5, 3, 2), (33, 2, 9), (17, 40, 27)):
+        inp, tgt = synthetic_maps(batch, size, 91), synthetic_maps(batch, size, 92)
+        cfg = O.sample_loss_configs(batch, n // 3 if n >= 3 else 1, n - (n // 3 if n >= 3 else 1)) if n > 1 \
+            else torch.tensor([[[0.3, -0.2, 1.5, -0.4, 0.1, 2.0, 30.0, 20.0, 10.0]]])
+        cfg = cfg[:, :n].contiguous()
+        l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+        loss, grad = ours_loss_and_grad(S, inp.numpy(), tgt.numpy(), cfg.numpy())
+        assert abs(loss - float(l64)) <= 5e-6 * float(l64), (size, batch, n)
+        assert parity.rel_l2(grad, g64.numpy()) <= 2e-4, (size, batch, n)

@@ -1,0 +1,57 @@
+"""CPU check of the kernels' algebra: csrc/shading.cuh compiled for the host (tests/emulation)
+against the golden fixtures of the unmodified reference, with the same three-way tolerances the
+GPU parity tests use.  Catches mistakes in the rearranged forward math and in the analytic adjoint
+without a GPU; the MUFU approximations themselves are only exercised by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as O
+from tests import parity
+from tests.emulation import host as emu
+
+
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27"])
+def test_loss_and_gradient_three_way(golden, fixture):
+    g = golden(fixture)
+    loss, grad = emu.loss_forward_backward(g["input"], g["target"], g["configs"])
+    parity.check_loss(loss, g["loss_f64"])
+    for row in parity.check_grad_groups(grad, g["grad_f32"], g["grad_f64"]):
+        print(fixture, row)
+
+
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress"])
+def test_renders_three_way(golden, fixture):
+    g = golden(fixture)
+    got = emu.render_forward(g["input"], g["configs"])
+    print(parity.check_tensor(got, g["renders_f32"], g["renders_f64"], "renders"))
+    # the quantity the loss consumes
+    dlog = np.abs(np.log(got.astype(np.float64) + 0.1) - np.log(g["renders_f64"] + 0.1)).max()
+    assert dlog < 2e-3, dlog
+
+
+def test_render_fixed_scenes(golden):
+    g = golden("render_fixed")
+    got = emu.render_forward(g["maps"], g["configs"])            # [B,2,3,H,W], one shared scene list
+    ref32 = np.moveaxis(g["render4d_f32"], 0, 1)
+    ref64 = np.moveaxis(g["render4d_f64"], 0, 1)
+    parity.check_tensor(got, ref32, ref64, "render_fixed")
+
+
+def test_render_backward_matches_oracle_autograd(golden):
+    g = golden("loss_stress")
+    maps = torch.from_numpy(g["input"]).double().requires_grad_(True)
+    cfg = torch.from_numpy(g["configs"])
+    gen = torch.Generator().manual_seed(5)
+    w = torch.randn(maps.shape[0], cfg.shape[1], 3, maps.shape[2], maps.shape[3], generator=gen)
+    (O.render_batch(maps, cfg) * w.double()).sum().backward()
+    maps32 = torch.from_numpy(g["input"]).requires_grad_(True)
+    (O.render_batch(maps32, cfg) * w).sum().backward()
+    got = emu.render_backward(g["input"], g["configs"], w.numpy())
+    parity.check_grad_groups(got, maps32.grad.numpy(), maps.grad.numpy(), "render_bwd")
+
+
+def test_identical_maps_give_zero_loss_and_gradient(golden):
+    g = golden("loss_bench")
+    loss, grad = emu.loss_forward_backward(g["input"], g["input"], g["configs"])
+    assert loss == 0.0 and not grad.any()
