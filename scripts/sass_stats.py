@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Static SASS statistics of the kernels (no GPU needed): registers per kernel and the instruction
+mix of the innermost scene-record loop (the hot loop: from the first backward-branch target to the
+branch).  Usage: python scripts/sass_stats.py [kernel-name-regex]"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "svbrdf_estimation_b200", "csrc", "kernels.cu")
+OUT = os.path.join(ROOT, "build", "kernels.cubin")
+
+
+def main():
+    pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else r"loss_kernel.*Lb1ELb0ELi796")
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    p = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                        "-Xptxas", "-v", "-cubin", "-o", OUT, SRC], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode:
+        print(p.stdout)
+        return 1
+    regs = {}
+    cur = None
+    for line in p.stdout.splitlines():
+        m = re.search(r"Compiling entry function '(\S+)'", line)
+        if m:
+            cur = m.group(1)
+        m = re.search(r"Used (\d+) registers", line)
+        if m and cur:
+            regs[cur] = (int(m.group(1)), "spill" if "spill" in line else "")
+        if "bytes spill" in line and cur and not line.strip().startswith("0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads"):
+            print("SPILL in", cur, line.strip())
+    sass = subprocess.run(["cuobjdump", "-sass", OUT], stdout=subprocess.PIPE, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    for f in funcs:
+        name = f.split("\n", 1)[0].strip()
+        if not pat.search(name):
+            continue
+        ins = re.findall(r"/\*([0-9a-f]{4,5})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)\s*([^;]*);", f)
+        addr = {int(a, 16): i for i, (a, _, _) in enumerate(ins)}
+        loops = []
+        for i, (a, op, args) in enumerate(ins):
+            if op.startswith("BRA"):
+                m = re.search(r"0x([0-9a-f]+)", args)
+                if m and int(m.group(1), 16) in addr and addr[int(m.group(1), 16)] < i:
+                    loops.append((addr[int(m.group(1), 16)], i))
+        print("== %s: %d registers, %d instructions total" % (name[:110], regs.get(name, (0, ""))[0], len(ins)))
+        for (s, e) in loops:
+            body = ins[s:e + 1]
+            mix = collections.Counter(op.split(".")[0] for _, op, _ in body)
+            fma_pipe = sum(v for k, v in mix.items() if k in ("FFMA", "FMUL", "FADD"))
+            fma2 = sum(v for k, v in mix.items() if k in ("FFMA2", "FMUL2", "FADD2"))
+            alu = sum(v for k, v in mix.items() if k in ("FMNMX", "FSEL", "FSETP", "LOP3", "IADD3", "MOV", "SEL", "ISETP", "PRMT", "SHF", "IMAD"))
+            print("   loop [%d..%d] %d instr: packed-FP %d, scalar-FP %d, MUFU %d, ALU-ish %d | %s" % (
+                s, e, len(body), fma2, fma_pipe, mix.get("MUFU", 0), alu,
+                ", ".join("%s %d" % kv for kv in mix.most_common())))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -127,7 +127,7 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
     int rc = 0, prev = -1;
     cudaGetDevice(&prev);
     const int HW = c->H * c->W;
-    const int cpi = (HW + 255) / 256;
+    const int cpi = svb_ctas_per_image(HW, c->W);
     float* part_render = c->d_ws;
     float* part_l1 = c->d_ws + (size_t)B * cpi;
     // slices: enough to overlap the two copy directions with compute, not so many that launch
@@ -151,7 +151,7 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
                 CK(cudaMemcpyAsync(grad_host + off, c->d_gr + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        rc = svb_launch_finalize(part_render, part_l1, B, HW, N, false, 0.f, c->d_loss, 1, c->s_comp);
+        rc = svb_launch_finalize(part_render, part_l1, B, HW, c->W, N, false, 0.f, c->d_loss, 1, c->s_comp);
         if (rc) goto done;
         CK(cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
         CK(cudaStreamSynchronize(c->s_comp));

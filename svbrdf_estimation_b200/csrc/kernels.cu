@@ -1,14 +1,16 @@
 // kernels.cu - sm_100a kernels of the rendering-loss path and their C-ABI launchers.
 //
 // Work decomposition (DESIGN.md "Kernels"):
-//   grid = (ceil(H*W / 256), batch elements of this launch), 256 threads, ONE pixel per thread.
-//   A thread loads its pixel's 12 (+12 target) channels with coalesced 32-bit loads (a warp reads
-//   128 contiguous bytes of each of the 24 planes), keeps them and the 12 gradient accumulators in
-//   registers, loops over the N scene records of its batch element - which live in the kernel
-//   parameter block (constant bank, warp-uniform addresses, no scene upload) - and never writes a
-//   per-record intermediate to memory.  The log-L1 terms are reduced thread -> warp (shuffle) ->
-//   CTA (shared memory) -> one partial per CTA; a 1-CTA finalize kernel adds the partials in a
-//   fixed order in fp64, so the loss is run-to-run deterministic and uses no float atomics.
+//   grid = (ceil(H*W / (threads * lanes)), batch elements of this launch).  A thread owns `lanes`
+//   horizontally adjacent pixels: 2 when W is even (lane type F2: packed FADD2/FMUL2/FFMA2 math,
+//   64-bit coalesced loads/stores), 1 otherwise.  It loads its pixels' 12 (+12 target) channels once
+//   (a warp reads 128/256 contiguous bytes of each of the 24 planes), keeps them and the 12 gradient
+//   accumulators in registers, loops over the N scene records of its batch element - which live in
+//   the kernel parameter block (constant bank, warp-uniform addresses, no scene upload) - and never
+//   writes a per-record intermediate to memory.  The log-L1 terms are reduced thread -> warp
+//   (shuffle) -> CTA (shared memory) -> one partial per CTA; a 1-CTA finalize kernel adds the
+//   partials in a fixed order in fp64, so the loss is run-to-run deterministic and uses no float
+//   atomics.
 //
 // Reference semantics: LocalRenderer.render renderers.py:67-104, RenderingLoss.forward
 // losses.py:29-52, SVBRDFL1Loss/MixedLoss losses.py:7-19,54-63 (paths relative to
@@ -24,12 +26,16 @@
 
 namespace svb {
 
-constexpr int kThreads = 256;
 constexpr int kRecFloats = 9;
 // Kernel parameters may total 32,764 bytes on sm_70+ with CUDA >= 12.1.  Two capacities keep the
 // parameter copy small for the common render(scene, maps) call.
 constexpr int kCapSmall = 64;    // records ->  2,304 B
 constexpr int kCapLarge = 796;   // records -> 28,656 B
+
+// threads per CTA by lane type (the packed kernels hold two pixels of state per thread)
+template <typename T> struct Cfg;
+template <> struct Cfg<float> { static constexpr int kThreads = 256; };
+template <> struct Cfg<F2> { static constexpr int kThreads = 128; };
 
 template <int CAP>
 struct SceneBlock {
@@ -57,6 +63,36 @@ struct RenderArgs {
     int HW, W, N, per_batch;
 };
 
+// ---- lane-typed global memory access -------------------------------------------------------------
+__device__ __forceinline__ void ld_lane(const float* p, float& v) { v = __ldg(p); }
+__device__ __forceinline__ void ld_lane(const float* p, F2& v) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v = mk2(t.x, t.y);
+}
+__device__ __forceinline__ void ld_stream(const float* p, float& v) { v = __ldcs(p); }
+__device__ __forceinline__ void ld_stream(const float* p, F2& v) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    v = mk2(t.x, t.y);
+}
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float* p, F2 v) { __stcs(reinterpret_cast<float2*>(p), make_float2(lo(v), hi(v))); }
+
+template <typename T>
+__device__ __forceinline__ void load12(const float* __restrict__ base, int HW, T (&v)[12]) {
+#pragma unroll
+    for (int c = 0; c < 12; ++c) ld_lane(base + (size_t)c * HW, v[c]);
+}
+template <typename T>
+__device__ __forceinline__ void store12(float* __restrict__ base, int HW, const T (&v)[12]) {
+#pragma unroll
+    for (int c = 0; c < 12; ++c) st_stream(base + (size_t)c * HW, v[c]);
+}
+
+__device__ __forceinline__ bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
+__device__ __forceinline__ bool same3(const F2 (&v)[12]) {
+    return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -64,7 +100,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Sum over the CTA; result valid in thread 0.  Fixed order => deterministic.
-__device__ __forceinline__ float cta_sum(float v, float* smem /* [kThreads/32] */) {
+template <int THREADS>
+__device__ __forceinline__ float cta_sum(float v, float* smem /* [THREADS/32] */) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) smem[warp] = v;
@@ -72,110 +109,155 @@ __device__ __forceinline__ float cta_sum(float v, float* smem /* [kThreads/32] *
     float t = 0.f;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) t += smem[w];
+        for (int w = 0; w < THREADS / 32; ++w) t += smem[w];
     }
     __syncthreads();
     return t;
 }
 
-__device__ __forceinline__ void load12(const float* __restrict__ base, int HW, float (&v)[12]) {
-#pragma unroll
-    for (int c = 0; c < 12; ++c) v[c] = __ldg(base + (size_t)c * HW);
+// Pixel bookkeeping shared by all kernels: first pixel of this thread, its coordinates.
+template <typename T>
+struct Where {
+    bool live;
+    int p;        // first pixel (clamped into the image for dead threads)
+    T x;          // lin[col] per lane      (renderers.py:73-76)
+    float y;      // -lin[row]
+};
+template <typename T>
+__device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restrict__ lin) {
+    constexpr int L = LaneTraits<T>::kLanes;
+    Where<T> w;
+    const int pix = (blockIdx.x * Cfg<T>::kThreads + threadIdx.x) * L;
+    w.live = pix < HW;
+    w.p = w.live ? pix : HW - L;
+    const int row = w.p / W, col = w.p - row * W;
+    ld_lane(lin + col, w.x);
+    w.y = -__ldg(lin + row);
+    return w;
 }
 
-__device__ __forceinline__ bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
-
 // ---------------------------------------------------------------------------------------------
-// RenderingLoss / MixedLoss: forward (+ backward) for one pixel over all N records
+// RenderingLoss / MixedLoss: forward (+ backward) for one thread's pixels over all N records
 // ---------------------------------------------------------------------------------------------
-template <int RC, bool BWD>
-__device__ __forceinline__ float loss_pixel(const float (&vi)[12], const float (&vt)[12], float x, float y,
-                                            const float* __restrict__ rec, int N, float scale, float (&gout)[12]) {
-    const Pix<RC> pi = make_pix<RC>(vi);
-    const Pix<RC> pt = make_pix<RC>(vt);
-    Acc acc;
-    acc_zero(acc);
-    float lsum = 0.f;
+// C0 = first colour channel of the pass (0 for NC = 3; the pass's channel for NC = 1).
+template <typename T, int NC, int C0, bool BWD>
+__device__ __forceinline__ T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
+                                          const float* __restrict__ rec, int N, Acc<T, NC>& acc) {
+    T lsum = LaneTraits<T>::splat(0.f);
 #pragma unroll 1
     for (int k = 0; k < N; ++k, rec += kRecFloats) {
-        const Geo g = make_geo(x, y, rec);
-        Fwd<RC> fi, ft;
-        shade_fwd<RC, BWD>(g, pi, fi);
-        shade_fwd<RC, BWD>(g, pt, ft);   // same arithmetic as the input map: identical maps give exactly 0
-        const float E[3] = {g.e0, g.e1, g.e2};
-        float A[3];
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        Fwd<T, NC> fi, ft;
+        shade_fwd<T, NC, BWD>(g, pi, fi);
+        shade_fwd<T, NC, BWD>(g, pt, ft);   // same arithmetic as the input map: identical maps give exactly 0
+        T AE[NC];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float xi = fmaf(fi.f[c], E[c] * fi.LN0, kEpsRender);   // radiance + 0.1 (losses.py:46-47)
-            const float xt = fmaf(ft.f[c], E[c] * ft.LN0, kEpsRender);
-            const float d = mufu_lg2(xi) - mufu_lg2(xt);                 // log2 units; ln2 applied at the end
-            lsum += fabsf(d);
-            if (BWD) {
-                const float ix = mufu_rcp(xi);
-                A[c] = (d > 0.f) ? ix : ((d < 0.f) ? -ix : 0.f);         // sign(0) = 0 like torch (losses.py:50)
-            }
+        for (int c = 0; c < NC; ++c) {
+            const T E = g.fall * rec[6 + C0 + c];                          // light colour * falloff
+            const T xi = vfma(fi.f[c], E * fi.LN0, kEpsRender);            // radiance + 0.1 (losses.py:46-47)
+            const T xt = vfma(ft.f[c], E * ft.LN0, kEpsRender);
+            const T d = vlg2(xi) - vlg2(xt);                               // log2 units; ln2 applied at the end
+            lsum = lsum + vabs(d);
+            if (BWD) AE[c] = vsigned(d, vrcp(xi)) * E;                     // sign(0) = 0 like torch (losses.py:50)
         }
-        if (BWD) shade_bwd<RC>(g, pi, fi, A, acc);
+        if (BWD) shade_bwd<T, NC>(g, pi, fi, AE, acc);
     }
-    if (BWD) acc_to_grad<RC>(acc, pi, scale, gout);
     return lsum;
 }
 
-// Map-space L1 terms of SVBRDFL1Loss (losses.py:7-19) for one pixel; adds their gradient.
-template <bool BWD>
-__device__ __forceinline__ float l1_pixel(const float (&vi)[12], const float (&vt)[12], float scale, float (&gout)[12]) {
-    float s = 0.f;
+// One single-channel pass (general roughness): channel C of input/target with its own roughness.
+template <typename T, int C, bool BWD>
+__device__ __forceinline__ T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y,
+                                               const float* __restrict__ rec, int N, float scale, T (&g)[12]) {
+    const Pix<T, 1> pi = make_pix<T, 1>(&vi[0], &vi[3 + C], &vi[9 + C], vi[6 + C]);
+    const Pix<T, 1> pt = make_pix<T, 1>(&vt[0], &vt[3 + C], &vt[9 + C], vt[6 + C]);
+    Acc<T, 1> acc;
+    acc_zero(acc);
+    const T l = loss_records<T, 1, C, BWD>(pi, pt, x, y, rec, N, acc);
+    if (BWD) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j] * scale;
+        g[3 + C] = acc.gd[0] * (scale * kInvPi);
+        g[6 + C] = (acc.ga2[0] * scale) * rough_chain(vi[6 + C]);
+        g[9 + C] = acc.gs[0] * scale;
+    }
+    return l;
+}
+
+template <typename T, bool BWD>
+__device__ __forceinline__ T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y,
+                                        const float* __restrict__ rec, int N, float scale, T (&g)[12]) {
+    // fast path: the warp's pixels all carry one roughness value replicated on the three channels
+    if (__all_sync(0xffffffffu, same3(vi) && same3(vt))) {
+        const Pix<T, 3> pi = make_pix<T, 3>(&vi[0], &vi[3], &vi[9], vi[6]);
+        const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
+        Acc<T, 3> acc;
+        acc_zero(acc);
+        const T l = loss_records<T, 3, 0, BWD>(pi, pt, x, y, rec, N, acc);
+        if (BWD) {
+            const T chain = rough_chain(vi[6]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g[c] = acc.gn[c] * scale;
+                g[3 + c] = acc.gd[c] * (scale * kInvPi);
+                g[6 + c] = (acc.ga2[c] * scale) * chain;
+                g[9 + c] = acc.gs[c] * scale;
+            }
+        }
+        return l;
+    }
+    // general path: three single-channel passes (the loss and all gradients decompose by colour channel)
+    if (BWD) { g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f); }
+    T l = loss_channel_pass<T, 0, BWD>(vi, vt, x, y, rec, N, scale, g);
+    l = l + loss_channel_pass<T, 1, BWD>(vi, vt, x, y, rec, N, scale, g);
+    l = l + loss_channel_pass<T, 2, BWD>(vi, vt, x, y, rec, N, scale, g);
+    return l;
+}
+
+// Map-space L1 terms of SVBRDFL1Loss (losses.py:7-19) for one thread's pixels; adds their gradient.
+template <typename T, bool BWD>
+__device__ __forceinline__ T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]) {
+    T s = LaneTraits<T>::splat(0.f);
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
         const bool logged = (c >= 3 && c < 6) || c >= 9;      // diffuse and specular use log(x + 0.01)
-        float d, w = 1.f;
+        T d, w = LaneTraits<T>::splat(scale);
         if (logged) {
-            const float a = vi[c] + kEpsL1, b = vt[c] + kEpsL1;
-            d = (mufu_lg2(a) - mufu_lg2(b)) * kLn2;
-            if (BWD) w = mufu_rcp(a);
+            const T a = vi[c] + kEpsL1, b = vt[c] + kEpsL1;
+            d = (vlg2(a) - vlg2(b)) * kLn2;
+            if (BWD) w = vrcp(a) * scale;
         } else {
             d = vi[c] - vt[c];
         }
-        s += fabsf(d);
-        if (BWD) gout[c] += (d > 0.f) ? w * scale : ((d < 0.f) ? -w * scale : 0.f);
+        s = s + vabs(d);
+        if (BWD) g[c] = g[c] + vsigned(d, w);
     }
     return s;
 }
 
-template <bool BWD, bool MIXED, int CAP>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, bool BWD, bool MIXED, int CAP>
+__global__ void __launch_bounds__(Cfg<T>::kThreads)
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
-    __shared__ float red[kThreads / 32];
+    constexpr int THREADS = Cfg<T>::kThreads;
+    __shared__ float red[THREADS / 32];
     const int b = blockIdx.y;
-    const int pix = blockIdx.x * kThreads + threadIdx.x;
-    const bool live = pix < a.HW;
-    const int p = live ? pix : a.HW - 1;
-    const int row = p / a.W, col = p - row * a.W;
-    const float x = __ldg(a.lin + col), y = -__ldg(a.lin + row);   // renderers.py:73-76
-    const size_t off = (size_t)b * 12 * a.HW + p;
-    float vi[12], vt[12], g[12];
-    load12(a.input + off, a.HW, vi);
-    load12(a.target + off, a.HW, vt);
+    const Where<T> w = locate<T>(a.HW, a.W, a.lin);
+    const size_t off = (size_t)b * 12 * a.HW + w.p;
+    T vi[12], vt[12], g[12];
+    load12<T>(a.input + off, a.HW, vi);
+    load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
-    float lsum;
-    const bool shared_rough = same3(vi) && same3(vt);
-    if (__all_sync(0xffffffffu, shared_rough)) lsum = loss_pixel<1, BWD>(vi, vt, x, y, rec, a.N, a.scale_render, g);
-    else                                        lsum = loss_pixel<3, BWD>(vi, vt, x, y, rec, a.N, a.scale_render, g);
+    const T lsum = loss_pixel<T, BWD>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    T l1 = LaneTraits<T>::splat(0.f);
+    if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
+    if (BWD && w.live) store12<T>(a.grad + off, a.HW, g);
 
-    float l1 = 0.f;
-    if (MIXED) l1 = l1_pixel<BWD>(vi, vt, a.scale_l1, g);
-
-    if (BWD && live) {
-        float* gp = a.grad + off;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) __stcs(gp + (size_t)c * a.HW, g[c]);
-    }
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    const float tr = cta_sum(live ? lsum : 0.f, red);
+    const float tr = cta_sum<THREADS>(w.live ? hsum(lsum) : 0.f, red);
     if (threadIdx.x == 0) a.part_render[cta] = tr;
     if (MIXED) {
-        const float tl = cta_sum(live ? l1 : 0.f, red);
+        const float tl = cta_sum<THREADS>(w.live ? hsum(l1) : 0.f, red);
         if (threadIdx.x == 0) a.part_l1[cta] = tl;
     }
 }
@@ -186,9 +268,17 @@ finalize_kernel(const float* __restrict__ part_render, const float* __restrict__
                 double mul_render, double mul_l1, float l1_weight, float* __restrict__ out, int n_out) {
     __shared__ double sm[2][32];
     double s0 = 0.0, s1 = 0.0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        s0 += (double)part_render[i];
-        if (part_l1) s1 += (double)part_l1[i];
+    // 8 independent loads in flight per thread; the summation order is fixed by (thread, i)
+    for (int base = threadIdx.x; base < count; base += 8 * 1024) {
+        float v[8], u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 1024;
+            v[j] = (i < count) ? __ldcg(part_render + i) : 0.f;
+            u[j] = (part_l1 && i < count) ? __ldcg(part_l1 + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0 += (double)v[j]; s1 += (double)u[j]; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -210,81 +300,106 @@ finalize_kernel(const float* __restrict__ part_render, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // LocalRenderer.render forward / backward
 // ---------------------------------------------------------------------------------------------
-template <int RC>
-__device__ __forceinline__ void render_pixel(const float (&v)[12], float x, float y, const float* __restrict__ rec,
-                                             int N, float* __restrict__ out, int HW, bool live) {
-    const Pix<RC> px = make_pix<RC>(v);
+template <typename T, int NC, int C0>
+__device__ __forceinline__ void render_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec,
+                                               int N, float* __restrict__ out, int HW, bool live) {
 #pragma unroll 1
     for (int k = 0; k < N; ++k, rec += kRecFloats, out += (size_t)3 * HW) {
-        const Geo g = make_geo(x, y, rec);
-        Fwd<RC> f;
-        shade_fwd<RC, false>(g, px, f);
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        Fwd<T, NC> f;
+        shade_fwd<T, NC, false>(g, px, f);
         if (live) {
-            __stcs(out, f.f[0] * (g.e0 * f.LN0));                // renderers.py:100
-            __stcs(out + HW, f.f[1] * (g.e1 * f.LN0));
-            __stcs(out + 2 * (size_t)HW, f.f[2] * (g.e2 * f.LN0));
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                st_stream(out + (size_t)(C0 + c) * HW, f.f[c] * ((g.fall * rec[6 + C0 + c]) * f.LN0));   // renderers.py:100
         }
     }
 }
 
-template <int CAP>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int CAP>
+__global__ void __launch_bounds__(Cfg<T>::kThreads)
 render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     const int b = blockIdx.y;
-    const int pix = blockIdx.x * kThreads + threadIdx.x;
-    const bool live = pix < a.HW;
-    const int p = live ? pix : a.HW - 1;
-    const int row = p / a.W, col = p - row * a.W;
-    const float x = __ldg(a.lin + col), y = -__ldg(a.lin + row);
-    float v[12];
-    load12(a.maps + (size_t)b * 12 * a.HW + p, a.HW, v);
+    const Where<T> w = locate<T>(a.HW, a.W, a.lin);
+    T v[12];
+    load12<T>(a.maps + (size_t)b * 12 * a.HW + w.p, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
-    float* out = a.images + (size_t)b * a.N * 3 * a.HW + p;
-    if (__all_sync(0xffffffffu, same3(v))) render_pixel<1>(v, x, y, rec, a.N, out, a.HW, live);
-    else                                   render_pixel<3>(v, x, y, rec, a.N, out, a.HW, live);
+    float* out = a.images + (size_t)b * a.N * 3 * a.HW + w.p;
+    if (__all_sync(0xffffffffu, same3(v))) {
+        render_records<T, 3, 0>(make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]), w.x, w.y, rec, a.N, out, a.HW, w.live);
+    } else {
+        render_records<T, 1, 0>(make_pix<T, 1>(&v[0], &v[3], &v[9], v[6]), w.x, w.y, rec, a.N, out, a.HW, w.live);
+        render_records<T, 1, 1>(make_pix<T, 1>(&v[0], &v[4], &v[10], v[7]), w.x, w.y, rec, a.N, out, a.HW, w.live);
+        render_records<T, 1, 2>(make_pix<T, 1>(&v[0], &v[5], &v[11], v[8]), w.x, w.y, rec, a.N, out, a.HW, w.live);
+    }
 }
 
-template <int RC>
-__device__ __forceinline__ void render_bwd_pixel(const float (&v)[12], float x, float y, const float* __restrict__ rec,
-                                                 int N, const float* __restrict__ gin, int HW, float (&gout)[12]) {
-    const Pix<RC> px = make_pix<RC>(v);
-    Acc acc;
-    acc_zero(acc);
+template <typename T, int NC, int C0>
+__device__ __forceinline__ void render_bwd_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec,
+                                                   int N, const float* __restrict__ gin, int HW, Acc<T, NC>& acc) {
 #pragma unroll 1
     for (int k = 0; k < N; ++k, rec += kRecFloats, gin += (size_t)3 * HW) {
-        const float A[3] = {__ldcs(gin), __ldcs(gin + HW), __ldcs(gin + 2 * (size_t)HW)};
-        const Geo g = make_geo(x, y, rec);
-        Fwd<RC> f;
-        shade_fwd<RC, true>(g, px, f);
-        shade_bwd<RC>(g, px, f, A, acc);
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        T AE[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            T a;
+            ld_stream(gin + (size_t)(C0 + c) * HW, a);
+            AE[c] = a * (g.fall * rec[6 + C0 + c]);
+        }
+        Fwd<T, NC> f;
+        shade_fwd<T, NC, true>(g, px, f);
+        shade_bwd<T, NC>(g, px, f, AE, acc);
     }
-    acc_to_grad<RC>(acc, px, 1.f, gout);
 }
 
-template <int CAP>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int C>
+__device__ __forceinline__ void render_bwd_channel_pass(const T (&v)[12], T x, float y, const float* __restrict__ rec,
+                                                        int N, const float* __restrict__ gin, int HW, T (&g)[12]) {
+    const Pix<T, 1> px = make_pix<T, 1>(&v[0], &v[3 + C], &v[9 + C], v[6 + C]);
+    Acc<T, 1> acc;
+    acc_zero(acc);
+    render_bwd_records<T, 1, C>(px, x, y, rec, N, gin, HW, acc);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j];
+    g[3 + C] = acc.gd[0] * kInvPi;
+    g[6 + C] = acc.ga2[0] * rough_chain(v[6 + C]);
+    g[9 + C] = acc.gs[0];
+}
+
+template <typename T, int CAP>
+__global__ void __launch_bounds__(Cfg<T>::kThreads)
 render_bwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     const int b = blockIdx.y;
-    const int pix = blockIdx.x * kThreads + threadIdx.x;
-    const bool live = pix < a.HW;
-    const int p = live ? pix : a.HW - 1;
-    const int row = p / a.W, col = p - row * a.W;
-    const float x = __ldg(a.lin + col), y = -__ldg(a.lin + row);
-    float v[12], g[12];
-    const size_t off = (size_t)b * 12 * a.HW + p;
-    load12(a.maps + off, a.HW, v);
+    const Where<T> w = locate<T>(a.HW, a.W, a.lin);
+    T v[12], g[12];
+    const size_t off = (size_t)b * 12 * a.HW + w.p;
+    load12<T>(a.maps + off, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
-    const float* gin = a.gimages + (size_t)b * a.N * 3 * a.HW + p;
-    if (__all_sync(0xffffffffu, same3(v))) render_bwd_pixel<1>(v, x, y, rec, a.N, gin, a.HW, g);
-    else                                   render_bwd_pixel<3>(v, x, y, rec, a.N, gin, a.HW, g);
-    if (live) {
-        float* gp = a.gmaps + off;
+    const float* gin = a.gimages + (size_t)b * a.N * 3 * a.HW + w.p;
+    if (__all_sync(0xffffffffu, same3(v))) {
+        const Pix<T, 3> px = make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]);
+        Acc<T, 3> acc;
+        acc_zero(acc);
+        render_bwd_records<T, 3, 0>(px, w.x, w.y, rec, a.N, gin, a.HW, acc);
+        const T chain = rough_chain(v[6]);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) __stcs(gp + (size_t)c * a.HW, g[c]);
+        for (int c = 0; c < 3; ++c) {
+            g[c] = acc.gn[c];
+            g[3 + c] = acc.gd[c] * kInvPi;
+            g[6 + c] = acc.ga2[c] * chain;
+            g[9 + c] = acc.gs[c];
+        }
+    } else {
+        g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f);
+        render_bwd_channel_pass<T, 0>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
+        render_bwd_channel_pass<T, 1>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
+        render_bwd_channel_pass<T, 2>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
     }
+    if (w.live) store12<T>(a.gmaps + off, a.HW, g);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 scale_kernel(float* __restrict__ g, size_t count, const float* __restrict__ upstream) {
     const float u = __ldg(upstream);
     if (u == 1.0f) return;                      // loss.backward(): nothing to do, decided on the device
@@ -296,7 +411,7 @@ scale_kernel(float* __restrict__ g, size_t count, const float* __restrict__ upst
 // FP32 throughput probes (bench.py: measured denominators for the FP32 roofline)
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 probe_kernel(int iters, float* __restrict__ sink) {
     float r[16];
 #pragma unroll
@@ -311,16 +426,16 @@ probe_kernel(int iters, float* __restrict__ sink) {
             } else if (KIND == 1) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    unsigned long long d, a2, m2, c2;
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(r[i]), "f"(r[i + 1]));
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(m2) : "f"(m));
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(c));
-                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a2), "l"(m2), "l"(c2));
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(r[i]), "=f"(r[i + 1]) : "l"(d));
+                    const F2 t = vfma(mk2(r[i], r[i + 1]), mk2(m, m), mk2(c, c));
+                    r[i] = lo(t); r[i + 1] = hi(t);
                 }
             } else if (KIND == 2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = mufu_rcp(r[i]);
+                for (int i = 0; i < 16; ++i) {       // volatile: each MUFU is issued (x -> 1/x -> x ...)
+                    float y;
+                    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r[i]));
+                    r[i] = y;
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) { r[i] = r[i] * m; r[i + 1] = r[i + 1] + c; }
@@ -330,7 +445,7 @@ probe_kernel(int iters, float* __restrict__ sink) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += r[i];
-    if (s == 123.456f) sink[blockIdx.x * kThreads + threadIdx.x] = s;   // keeps the chain alive
+    if (s == 123.456f) sink[blockIdx.x * 256 + threadIdx.x] = s;   // keeps the chain alive
 }
 
 }  // namespace svb
@@ -362,7 +477,11 @@ int svb_check_shape(int B, int H, int W, int N) {
     return 0;
 }
 
-static inline int ctas_per_image(int HW) { return (HW + kThreads - 1) / kThreads; }
+// Packed (two pixels per thread) kernels need pixel pairs that never straddle a row and 8-byte
+// aligned planes: W even (H == W, so H*W is even too).
+static inline bool use_packed(int W) { return (W & 1) == 0; }
+static inline int pixels_per_cta(int W) { return use_packed(W) ? 2 * Cfg<F2>::kThreads : Cfg<float>::kThreads; }
+int svb_ctas_per_image(int HW, int W) { return (HW + pixels_per_cta(W) - 1) / pixels_per_cta(W); }
 
 extern "C" int svbrdf_b200_abi_version(void) { return SVBRDF_B200_ABI_VERSION; }
 extern "C" const char* svbrdf_b200_last_error(void) { return g_err; }
@@ -370,7 +489,7 @@ extern "C" const char* svbrdf_b200_last_error(void) { return g_err; }
 extern "C" size_t svbrdf_b200_workspace_bytes(int B, int N, int H, int W) {
     (void)N;
     if (B <= 0 || H <= 0 || W <= 0) return 256;
-    const size_t ctas = (size_t)B * (size_t)ctas_per_image(H * W);
+    const size_t ctas = (size_t)B * (size_t)svb_ctas_per_image(H * W, W);
     return 2 * ctas * sizeof(float) + 256;     // render partials + map-L1 partials
 }
 
@@ -381,13 +500,27 @@ static inline int batch_per_launch(int N, int per_batch, int cap) {
     return bc > 65535 ? 65535 : bc;
 }
 
-template <int CAP, typename Args, typename Kernel>
+template <int CAP, int THREADS, typename Args, typename Kernel>
 static cudaError_t launch_with_scenes(Kernel kernel, dim3 grid, const Args& args, const float* recs, int nrec,
                                       cudaStream_t st) {
     SceneBlock<CAP> blk;
     memcpy(blk.v, recs, (size_t)nrec * kRecFloats * sizeof(float));
-    kernel<<<grid, kThreads, 0, st>>>(args, blk);
+    kernel<<<grid, THREADS, 0, st>>>(args, blk);
     return cudaGetLastError();
+}
+
+template <typename T, bool BWD, bool MIXED>
+static cudaError_t launch_loss(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, kCapSmall>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, kCapLarge>, grid, a, recs, nrec, st);
+}
+template <typename T>
+static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, const LossArgs& a, const float* recs,
+                                 int nrec, cudaStream_t st) {
+    if (bwd) return mixed ? launch_loss<T, true, true>(small, grid, a, recs, nrec, st)
+                          : launch_loss<T, true, false>(small, grid, a, recs, nrec, st);
+    return mixed ? launch_loss<T, false, true>(small, grid, a, recs, nrec, st)
+                 : launch_loss<T, false, false>(small, grid, a, recs, nrec, st);
 }
 
 // Enqueues the loss kernel for batch elements [b0, b0+bn) of a B-element problem (several launches if
@@ -395,7 +528,7 @@ static cudaError_t launch_with_scenes(Kernel kernel, dim3 grid, const Args& args
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
                           bool mixed, float l1_weight, int b0, int bn, cudaStream_t st) {
-    const int cpi = ctas_per_image(HW);
+    const int cpi = svb_ctas_per_image(HW, W);
     LossArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N;
     a.scale_render = (float)(1.0 / ((double)B * N * 3.0 * HW));
@@ -411,22 +544,17 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
         a.part_l1 = part_l1 + (size_t)s0 * cpi;
         const dim3 grid(cpi, bc);
         const float* recs = scenes + (size_t)s0 * N * kRecFloats;
-        cudaError_t e;
-#define SVB_LAUNCH(BWD, MIX)                                                                                 \
-    (small ? launch_with_scenes<kCapSmall>(loss_kernel<BWD, MIX, kCapSmall>, grid, a, recs, bc * N, st)     \
-           : launch_with_scenes<kCapLarge>(loss_kernel<BWD, MIX, kCapLarge>, grid, a, recs, bc * N, st))
-        if (grad) e = mixed ? SVB_LAUNCH(true, true) : SVB_LAUNCH(true, false);
-        else      e = mixed ? SVB_LAUNCH(false, true) : SVB_LAUNCH(false, false);
-#undef SVB_LAUNCH
+        const cudaError_t e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st)
+                                            : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st);
         if (e != cudaSuccess) return cuda_status(e, "loss_kernel launch");
     }
     return 0;
 }
 
 // Adds the per-CTA partials of a B-element problem in a fixed order (fp64) and writes the loss value(s).
-int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, int N, bool mixed,
+int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, int W, int N, bool mixed,
                         float l1_weight, float* out, int n_out, cudaStream_t st) {
-    const size_t total_ctas = (size_t)B * ctas_per_image(HW);
+    const size_t total_ctas = (size_t)B * svb_ctas_per_image(HW, W);
     // ln2 converts the log2 differences to natural log; 1/M is the mean of losses.py:50.
     const double mul_render = (double)kLn2 / ((double)B * N * 3.0 * HW);
     const double mul_l1 = 1.0 / ((double)B * 3.0 * HW);
@@ -444,11 +572,11 @@ static int loss_impl(const float* input, const float* target, int B, int H, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
     float* part_render = (float*)ws;
-    float* part_l1 = part_render + (size_t)B * ctas_per_image(HW);
+    float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, W);
     if (int e = svb_launch_loss_range(input, target, grad, B, HW, W, scenes, N, lin, part_render, part_l1, mixed,
                                       l1_weight, 0, B, st))
         return e;
-    return svb_launch_finalize(part_render, part_l1, B, HW, N, mixed, l1_weight, out, n_out, st);
+    return svb_launch_finalize(part_render, part_l1, B, HW, W, N, mixed, l1_weight, out, n_out, st);
 }
 
 extern "C" int svbrdf_b200_loss_forward(const float* input_dev, const float* target_dev, int B, int H, int W,
@@ -475,6 +603,17 @@ extern "C" int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, c
                      workspace_dev, workspace_bytes, true, l1_weight, stream);
 }
 
+template <typename T>
+static cudaError_t launch_render_t(bool backward, bool small, dim3 grid, const RenderArgs& a, const float* recs,
+                                   int nrec, cudaStream_t st) {
+    constexpr int TH = Cfg<T>::kThreads;
+    if (backward)
+        return small ? launch_with_scenes<kCapSmall, TH>(render_bwd_kernel<T, kCapSmall>, grid, a, recs, nrec, st)
+                     : launch_with_scenes<kCapLarge, TH>(render_bwd_kernel<T, kCapLarge>, grid, a, recs, nrec, st);
+    return small ? launch_with_scenes<kCapSmall, TH>(render_fwd_kernel<T, kCapSmall>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, TH>(render_fwd_kernel<T, kCapLarge>, grid, a, recs, nrec, st);
+}
+
 static int render_impl(const float* maps, int B, int H, int W, const float* scenes, int N, int per_batch,
                        const float* lin, float* images, const float* gimages, float* gmaps, void* stream) {
     if (int e = svb_check_shape(B, H, W, N)) return e;
@@ -482,7 +621,7 @@ static int render_impl(const float* maps, int B, int H, int W, const float* scen
     const bool backward = gmaps != nullptr;
     if (backward ? !gimages : !images) return fail(SVBRDF_E_INVALID, "null pointer argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int HW = H * W, cpi = ctas_per_image(HW);
+    const int HW = H * W, cpi = svb_ctas_per_image(HW, W);
     RenderArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N; a.per_batch = per_batch ? 1 : 0;
     const size_t nrec_total = per_batch ? (size_t)B * N : (size_t)N;
@@ -497,13 +636,8 @@ static int render_impl(const float* maps, int B, int H, int W, const float* scen
         const dim3 grid(cpi, bc);
         const float* recs = per_batch ? scenes + (size_t)b0 * N * kRecFloats : scenes;
         const int nrec = per_batch ? bc * N : N;
-        cudaError_t e;
-        if (backward)
-            e = small ? launch_with_scenes<kCapSmall>(render_bwd_kernel<kCapSmall>, grid, a, recs, nrec, st)
-                      : launch_with_scenes<kCapLarge>(render_bwd_kernel<kCapLarge>, grid, a, recs, nrec, st);
-        else
-            e = small ? launch_with_scenes<kCapSmall>(render_fwd_kernel<kCapSmall>, grid, a, recs, nrec, st)
-                      : launch_with_scenes<kCapLarge>(render_fwd_kernel<kCapLarge>, grid, a, recs, nrec, st);
+        const cudaError_t e = use_packed(W) ? launch_render_t<F2>(backward, small, grid, a, recs, nrec, st)
+                                            : launch_render_t<float>(backward, small, grid, a, recs, nrec, st);
         if (e != cudaSuccess) return cuda_status(e, backward ? "render_bwd_kernel launch" : "render_fwd_kernel launch");
     }
     return 0;
@@ -525,9 +659,9 @@ extern "C" int svbrdf_b200_render_backward(const float* maps_dev, int B, int H, 
 extern "C" int svbrdf_b200_scale_grad(float* grad_dev, size_t count, const float* upstream_dev, void* stream) {
     if (!grad_dev || !upstream_dev) return fail(SVBRDF_E_INVALID, "null pointer argument");
     if (count == 0) return 0;
-    size_t blocks = (count + kThreads * 8 - 1) / (kThreads * 8);
+    size_t blocks = (count + 256 * 8 - 1) / (256 * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    scale_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(grad_dev, count, upstream_dev);
+    scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_dev, count, upstream_dev);
     return cuda_status(cudaGetLastError(), "scale_kernel launch");
 }
 
@@ -535,12 +669,12 @@ extern "C" int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* 
                                         void* stream) {
     if (blocks <= 0 || iters <= 0 || !sink_dev) return fail(SVBRDF_E_INVALID, "bad probe arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    int ops = 8 * 16;   // unroll 8 x 16 registers, one counted op each (f32x2 counts 2 per instruction -> still 16)
+    int ops = 8 * 16;   // unroll 8 x 16 registers, one counted op each (an f32x2 instruction counts 2)
     switch (kind) {
-        case 0: probe_kernel<0><<<blocks, kThreads, 0, st>>>(iters, sink_dev); break;
-        case 1: probe_kernel<1><<<blocks, kThreads, 0, st>>>(iters, sink_dev); break;
-        case 2: probe_kernel<2><<<blocks, kThreads, 0, st>>>(iters, sink_dev); break;
-        case 3: probe_kernel<3><<<blocks, kThreads, 0, st>>>(iters, sink_dev); break;
+        case 0: probe_kernel<0><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
+        case 1: probe_kernel<1><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
+        case 2: probe_kernel<2><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
+        case 3: probe_kernel<3><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
         default: return fail(SVBRDF_E_INVALID, "unknown probe kind");
     }
     if (ops_per_thread_iter) *ops_per_thread_iter = ops;

@@ -16,8 +16,17 @@
 //   * divisions / square roots / logs are single MUFU operations (rcp/rsqrt/lg2 .approx.ftz,
 //     <= 2 ulp), the natural-log scale ln2 is applied once to the reduced loss.
 //
-// RC is the number of distinct roughness channels: the API carries three (utils.py:48-51) but
-// the model and the dataset always replicate one (utils.py:78-80); RC=1 is the fast path.
+// Two template axes:
+//   T  - the lane type: `float` (one pixel per thread) or `F2` (two horizontally adjacent pixels per
+//        thread, packed in a 64-bit register pair).  Blackwell's FADD2/FMUL2/FFMA2 execute one F2
+//        operation per issue slot, which is what lifts this issue-bound kernel: every add/mul/fma
+//        below is a single instruction for two pixels; only min/max/select/compare and the MUFU
+//        operations are issued per lane.
+//   NC - colour channels per pass: 3 (the three channels share one roughness value, which is what
+//        the model and the dataset always produce, utils.py:78-80) or 1 (one colour channel with
+//        its own roughness; the API allows three different roughness channels, utils.py:48-51, and
+//        the kernels then run three single-channel passes - the loss and every gradient decompose
+//        by colour channel).
 #pragma once
 #ifdef SVB_HOST_EMULATION
 // tests/emulation/ compiles this header with g++ to check the algebra (forward and adjoint) against
@@ -37,6 +46,7 @@ constexpr float kClamp = 1e-3f;        // renderers.py:26,48-52,87
 constexpr float kEpsRender = 0.1f;     // losses.py:46
 constexpr float kEpsL1 = 0.01f;        // losses.py:13
 
+// ---- scalar MUFU wrappers --------------------------------------------------------------------
 #ifdef SVB_HOST_EMULATION
 SVB_DEV float mufu_rcp(float x) { return 1.0f / x; }
 SVB_DEV float mufu_rsqrt(float x) { return 1.0f / sqrtf(x); }
@@ -47,187 +57,234 @@ SVB_DEV float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" 
 SVB_DEV float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
+// ---- the packed lane type -----------------------------------------------------------------------
+#ifdef SVB_HOST_EMULATION
+struct F2 { float x, y; };
+SVB_DEV F2 mk2(float a, float b) { return F2{a, b}; }
+SVB_DEV float lo(F2 a) { return a.x; }
+SVB_DEV float hi(F2 a) { return a.y; }
+SVB_DEV F2 operator+(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+SVB_DEV F2 operator-(F2 a, F2 b) { return F2{a.x - b.x, a.y - b.y}; }
+SVB_DEV F2 operator*(F2 a, F2 b) { return F2{a.x * b.x, a.y * b.y}; }
+SVB_DEV F2 vfma(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#else
+struct F2 { unsigned long long v; };
+SVB_DEV F2 mk2(float a, float b) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+SVB_DEV float lo(F2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); (void)y; return x; }
+SVB_DEV float hi(F2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); (void)x; return y; }
+SVB_DEV F2 operator+(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SVB_DEV F2 operator-(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SVB_DEV F2 operator*(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SVB_DEV F2 vfma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#endif
+// scalar (warp-uniform or literal) operands are broadcast; sm_100a SASS takes them as UR.F32 / immediates
+SVB_DEV F2 operator+(F2 a, float b) { return a + mk2(b, b); }
+SVB_DEV F2 operator-(F2 a, float b) { return a - mk2(b, b); }
+SVB_DEV F2 operator-(float a, F2 b) { return mk2(a, a) - b; }
+SVB_DEV F2 operator*(F2 a, float b) { return a * mk2(b, b); }
+SVB_DEV F2 operator*(float a, F2 b) { return mk2(a, a) * b; }
+SVB_DEV F2 vfma(F2 a, F2 b, float c) { return vfma(a, b, mk2(c, c)); }
+SVB_DEV F2 vfma(F2 a, float b, F2 c) { return vfma(a, mk2(b, b), c); }
+SVB_DEV F2 vfma(F2 a, float b, float c) { return vfma(a, mk2(b, b), mk2(c, c)); }
+SVB_DEV float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+
+// per-lane operations (no packed form in the ISA)
+struct B2 { bool x, y; };
+SVB_DEV float vneg(float a) { return -a; }
+SVB_DEV F2 vneg(F2 a) { return mk2(-lo(a), -hi(a)); }
+SVB_DEV float vmax(float a, float m) { return fmaxf(a, m); }
+SVB_DEV F2 vmax(F2 a, float m) { return mk2(fmaxf(lo(a), m), fmaxf(hi(a), m)); }
+SVB_DEV float vabs(float a) { return fabsf(a); }
+SVB_DEV F2 vabs(F2 a) { return mk2(fabsf(lo(a)), fabsf(hi(a))); }
+SVB_DEV float vrcp(float a) { return mufu_rcp(a); }
+SVB_DEV F2 vrcp(F2 a) { return mk2(mufu_rcp(lo(a)), mufu_rcp(hi(a))); }
+SVB_DEV float vrsqrt(float a) { return mufu_rsqrt(a); }
+SVB_DEV F2 vrsqrt(F2 a) { return mk2(mufu_rsqrt(lo(a)), mufu_rsqrt(hi(a))); }
+SVB_DEV float vlg2(float a) { return mufu_lg2(a); }
+SVB_DEV F2 vlg2(F2 a) { return mk2(mufu_lg2(lo(a)), mufu_lg2(hi(a))); }
+SVB_DEV bool vge(float a, float b) { return a >= b; }
+SVB_DEV B2 vge(F2 a, float b) { return B2{lo(a) >= b, hi(a) >= b}; }
+SVB_DEV float vsel(bool m, float a, float b) { return m ? a : b; }
+SVB_DEV F2 vsel(B2 m, F2 a, float b) { return mk2(m.x ? lo(a) : b, m.y ? hi(a) : b); }
+// sign(d) * v with sign(0) = 0 (torch.sign / l1_loss backward)
+SVB_DEV float vsigned(float d, float v) { return (d > 0.f) ? v : ((d < 0.f) ? -v : 0.f); }
+SVB_DEV F2 vsigned(F2 d, F2 v) { return mk2(vsigned(lo(d), lo(v)), vsigned(hi(d), hi(v))); }
+SVB_DEV float hsum(float a) { return a; }
+SVB_DEV float hsum(F2 a) { return lo(a) + hi(a); }
+
+template <typename T> struct LaneTraits;
+template <> struct LaneTraits<float> {
+    static constexpr int kLanes = 1;
+    typedef bool Mask;
+    static SVB_DEV float splat(float c) { return c; }
+};
+template <> struct LaneTraits<F2> {
+    static constexpr int kLanes = 2;
+    typedef B2 Mask;
+    static SVB_DEV F2 splat(float c) { return mk2(c, c); }
+};
+
 // ---- per (pixel, scene record): map-independent geometry ---------------------------------------
+template <typename T>
 struct Geo {
-    float wix, wiy, wiz;   // unit vector to the light          (renderers.py:91-93)
-    float wox, woy, woz;   // unit vector to the camera         (renderers.py:79-82)
-    float ih;              // 1 / |wi + wo|                      (renderers.py:45)
-    float p5, omp5;        // (1-VH)^5 and its complement        (renderers.py:32,49)
-    float e0, e1, e2;      // light colour * 1/dist^2            (renderers.py:98-100)
+    T wix, wiy, wiz;   // unit vector to the light          (renderers.py:91-93)
+    T wox, woy, woz;   // unit vector to the camera         (renderers.py:79-82)
+    T ih;              // 1 / |wi + wo|                      (renderers.py:45)
+    T p5, omp5;        // (1-VH)^5 and its complement        (renderers.py:32,49)
+    T fall;            // 1 / |light - p|^2                  (renderers.py:99)
 };
 
 // s points at one scene record (9 floats: camera xyz, light xyz, colour rgb) in the constant bank.
-SVB_DEV Geo make_geo(float x, float y, const float* __restrict__ s) {
-    Geo g;
-    const float lx = s[3] - x, ly = s[4] - y, lz = s[5];
-    const float il = mufu_rsqrt(fmaf(lx, lx, fmaf(ly, ly, lz * lz)));
-    g.wix = lx * il; g.wiy = ly * il; g.wiz = lz * il;
-    const float fall = il * il;
-    g.e0 = s[6] * fall; g.e1 = s[7] * fall; g.e2 = s[8] * fall;
-    const float vx = s[0] - x, vy = s[1] - y, vz = s[2];
-    const float iv = mufu_rsqrt(fmaf(vx, vx, fmaf(vy, vy, vz * vz)));
-    g.wox = vx * iv; g.woy = vy * iv; g.woz = vz * iv;
-    const float c = fmaf(g.wix, g.wox, fmaf(g.wiy, g.woy, g.wiz * g.woz));
-    const float t = fmaf(2.f, c, 2.f);                 // |wi+wo|^2
-    g.ih = mufu_rsqrt(t);
-    const float vh = fmaxf(0.5f * t * g.ih, kClamp);   // wo.h = (1+c)/|wi+wo|, clamped (renderers.py:49)
-    const float m = 1.f - vh, m2 = m * m;
-    g.p5 = m2 * m2 * m;
+// x is per lane; y is the row coordinate (the lanes of an F2 are horizontal neighbours).
+template <typename T>
+SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
+    Geo<T> g;
+    const float ly = s[4] - y, lz = s[5], vy = s[1] - y, vz = s[2];
+    const float lyz = fmaf(ly, ly, lz * lz), vyz = fmaf(vy, vy, vz * vz);     // shared by the lanes
+    const T lx = LaneTraits<T>::splat(s[3]) - x;
+    const T il = vrsqrt(vfma(lx, lx, lyz));
+    g.wix = lx * il; g.wiy = il * ly; g.wiz = il * lz;
+    g.fall = il * il;
+    const T vx = LaneTraits<T>::splat(s[0]) - x;
+    const T iv = vrsqrt(vfma(vx, vx, vyz));
+    g.wox = vx * iv; g.woy = iv * vy; g.woz = iv * vz;
+    const T c = vfma(g.wix, g.wox, vfma(g.wiy, g.woy, g.wiz * g.woz));
+    const T t = vfma(c, 2.f, 2.f);                          // |wi+wo|^2
+    g.ih = vrsqrt(t);
+    const T vh = vmax((t * g.ih) * 0.5f, kClamp);           // wo.h = (1+c)/|wi+wo|, clamped (renderers.py:49)
+    const T m = 1.f - vh, m2 = m * m;
+    g.p5 = (m2 * m2) * m;
     g.omp5 = 1.f - g.p5;
     return g;
 }
 
 // ---- per pixel: quantities of one SVBRDF map that do not depend on the scene record ----------
-template <int RC>
+template <typename T, int NC>
 struct Pix {
-    float nx, ny, nz;      // normal, used as given (not re-normalised; renderers.py:84)
-    float kd[3];           // diffuse / pi                        (renderers.py:18-20)
-    float s[3];            // specular albedo
-    float a2[RC];          // alpha^2 = clamp(rough,1e-3)^4       (renderers.py:23-24,87)
-    float oma2[RC];        // 1 - alpha^2
-    float rg[RC];          // clamp(rough) where the clamp passes gradient, else 0
+    T nx, ny, nz;      // normal, used as given (not re-normalised; renderers.py:84)
+    T kd[NC];          // diffuse / pi                        (renderers.py:18-20)
+    T s[NC];           // specular albedo
+    T a2;              // alpha^2 = clamp(rough,1e-3)^4       (renderers.py:23-24,87)
+    T oma2;            // 1 - alpha^2
 };
 
-// v[12] = the pixel's 12 channels in API order.
-template <int RC>
-SVB_DEV Pix<RC> make_pix(const float (&v)[12]) {
-    Pix<RC> p;
-    p.nx = v[0]; p.ny = v[1]; p.nz = v[2];
+// n[3] normals; d, s: NC diffuse / specular channels; rough: the roughness channel of this pass.
+template <typename T, int NC>
+SVB_DEV Pix<T, NC> make_pix(const T* n, const T* d, const T* s, T rough) {
+    Pix<T, NC> p;
+    p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { p.kd[c] = v[3 + c] * kInvPi; p.s[c] = v[9 + c]; }
-#pragma unroll
-    for (int j = 0; j < RC; ++j) {
-        const float r = fmaxf(v[6 + j], kClamp);
-        const float a = r * r;
-        p.a2[j] = a * a;
-        p.oma2[j] = 1.f - p.a2[j];
-        p.rg[j] = (v[6 + j] >= kClamp) ? r : 0.f;       // clamp(min) passes gradient at equality
-    }
+    for (int c = 0; c < NC; ++c) { p.kd[c] = d[c] * kInvPi; p.s[c] = s[c]; }
+    const T r = vmax(rough, kClamp);
+    const T a = r * r;
+    p.a2 = a * a;
+    p.oma2 = 1.f - p.a2;
     return p;
 }
 
 // ---- forward shading of one map under one scene record -----------------------------------------
-template <int RC>
+template <typename T, int NC>
 struct Fwd {
-    float NHr, VNr, LNr;           // unclamped dots (for the clamp masks)
-    float NH, VN, LN, LN0;
-    float NH2, VN2, LN2;
-    float q[RC];                   // GGX denominator before the clamp
-    float iq[RC], zV[RC], zL[RC];  // 1/q, 1/(wV (VN+wV)), 1/(wL (LN+wL))   (BWD only)
-    float wV[RC], wL[RC];
-    float iR[RC];                  // 1 / (pi q^2 (VN+wV)(LN+wL))
-    float S[RC];                   // G D / (4 VN LN)
-    float F[3], f[3], Smkd[3];     // Fresnel, BRDF value, S - kd
+    T NHr, VNr, LNr;       // unclamped dots (for the clamp masks)
+    T NH, VN, LN, LN0;
+    T NH2, VN2, LN2;
+    T q;                   // GGX denominator before the clamp
+    T iq, zV, zL;          // 1/q, 1/(wV (VN+wV)), 1/(wL (LN+wL))
+    T wV, wL;
+    T iR;                  // 1 / (pi q^2 (VN+wV)(LN+wL))
+    T S;                   // G D / (4 VN LN)
+    T F[NC], f[NC], Smkd[NC];   // Fresnel, BRDF value, S - kd
 };
 
-template <int RC, bool BWD>
-SVB_DEV void shade_fwd(const Geo& g, const Pix<RC>& p, Fwd<RC>& o) {
-    o.LNr = fmaf(p.nx, g.wix, fmaf(p.ny, g.wiy, p.nz * g.wiz));
-    o.VNr = fmaf(p.nx, g.wox, fmaf(p.ny, g.woy, p.nz * g.woz));
+template <typename T, int NC, bool BWD>
+SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T, NC>& o) {
+    o.LNr = vfma(p.nx, g.wix, vfma(p.ny, g.wiy, p.nz * g.wiz));
+    o.VNr = vfma(p.nx, g.wox, vfma(p.ny, g.woy, p.nz * g.woz));
     o.NHr = (o.LNr + o.VNr) * g.ih;
-    o.NH = fmaxf(o.NHr, kClamp); o.VN = fmaxf(o.VNr, kClamp); o.LN = fmaxf(o.LNr, kClamp);
-    o.LN0 = fmaxf(o.LNr, 0.f);                                    // renderers.py:96
+    o.NH = vmax(o.NHr, kClamp); o.VN = vmax(o.VNr, kClamp); o.LN = vmax(o.LNr, kClamp);
+    o.LN0 = vmax(o.LNr, 0.f);                                     // renderers.py:96
     o.NH2 = o.NH * o.NH; o.VN2 = o.VN * o.VN; o.LN2 = o.LN * o.LN;
-#pragma unroll
-    for (int j = 0; j < RC; ++j) {
-        o.q[j] = fmaf(o.NH2, -p.oma2[j], 1.f);                    // NH^2 a2 + 1 - NH^2 (renderers.py:26)
-        const float qc = fmaxf(o.q[j], kClamp);
-        const float tV = fmaf(o.VN2, p.oma2[j], p.a2[j]);
-        const float tL = fmaf(o.LN2, p.oma2[j], p.a2[j]);
-        const float rwV = mufu_rsqrt(tV), rwL = mufu_rsqrt(tL);
-        o.wV[j] = tV * rwV; o.wL[j] = tL * rwL;
-        const float PV = o.VN + o.wV[j], PL = o.LN + o.wL[j];
-        if (BWD) {
-            const float iq = mufu_rcp(qc), iPV = mufu_rcp(PV), iPL = mufu_rcp(PL);
-            o.iq[j] = iq; o.zV[j] = rwV * iPV; o.zL[j] = rwL * iPL;
-            o.iR[j] = (iq * iq) * (iPV * iPL) * kInvPi;
-        } else {
-            o.iR[j] = mufu_rcp((qc * qc) * (PV * PL)) * kInvPi;
-        }
-        o.S[j] = p.a2[j] * o.iR[j];
+    o.q = 1.f - o.NH2 * p.oma2;                                   // NH^2 a2 + 1 - NH^2 (renderers.py:26)
+    const T qc = vmax(o.q, kClamp);
+    const T tV = vfma(o.VN2, p.oma2, p.a2);
+    const T tL = vfma(o.LN2, p.oma2, p.a2);
+    const T rwV = vrsqrt(tV), rwL = vrsqrt(tL);
+    o.wV = tV * rwV; o.wL = tL * rwL;
+    const T PV = o.VN + o.wV, PL = o.LN + o.wL;
+    if (BWD) {
+        const T iq = vrcp(qc), iPV = vrcp(PV), iPL = vrcp(PL);
+        o.iq = iq; o.zV = rwV * iPV; o.zL = rwL * iPL;
+        o.iR = ((iq * iq) * (iPV * iPL)) * kInvPi;
+    } else {
+        o.iR = vrcp((qc * qc) * (PV * PL)) * kInvPi;
     }
+    o.S = p.a2 * o.iR;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int j = (RC == 1) ? 0 : c;
-        o.F[c] = fmaf(p.s[c], g.omp5, g.p5);                      // s + (1-s)(1-VH)^5 (renderers.py:32)
-        o.Smkd[c] = o.S[j] - p.kd[c];
-        o.f[c] = fmaf(o.F[c], o.Smkd[c], p.kd[c]);                // (1-F) kd + F S     (renderers.py:62-65)
+    for (int c = 0; c < NC; ++c) {
+        o.F[c] = vfma(p.s[c], g.omp5, g.p5);                      // s + (1-s)(1-VH)^5 (renderers.py:32)
+        o.Smkd[c] = o.S - p.kd[c];
+        o.f[c] = vfma(o.F[c], o.Smkd[c], p.kd[c]);                // (1-F) kd + F S     (renderers.py:62-65)
     }
 }
 
 // ---- gradient accumulators of one pixel (summed over scene records) ----------------------------
+template <typename T, int NC>
 struct Acc {
-    float gn[3], gd[3], gs[3], ga2[3];
+    T gn[3], gd[NC], gs[NC], ga2[NC];
 };
-SVB_DEV void acc_zero(Acc& a) {
+template <typename T, int NC>
+SVB_DEV void acc_zero(Acc<T, NC>& a) {
+    const T z = LaneTraits<T>::splat(0.f);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { a.gn[c] = 0.f; a.gd[c] = 0.f; a.gs[c] = 0.f; a.ga2[c] = 0.f; }
+    for (int c = 0; c < 3; ++c) a.gn[c] = z;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { a.gd[c] = z; a.gs[c] = z; a.ga2[c] = z; }
 }
 
-// A[c] = d loss / d radiance_c for this (pixel, record).  Adds the adjoint of shade_fwd + the
-// radiance product (renderers.py:96-100) into acc.  gd is accumulated w.r.t. kd*pi ... i.e. the
-// caller multiplies acc.gd by 1/pi once per pixel.
-template <int RC>
-SVB_DEV void shade_bwd(const Geo& g, const Pix<RC>& p, const Fwd<RC>& o,
-                                          const float (&A)[3], Acc& acc) {
-    const float E[3] = {g.e0, g.e1, g.e2};
-    float T[RC], G[RC];
+// AE[c] = (d loss / d radiance_c) * E_c for this (pixel, record), E_c = light colour_c * falloff.
+// Adds the adjoint of shade_fwd and of the radiance product (renderers.py:96-100) into acc.
+// acc.gd is w.r.t. kd = diffuse/pi: the caller multiplies by 1/pi once per pixel.
+template <typename T, int NC>
+SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T, NC>& o, const T (&AE)[NC],
+                       Acc<T, NC>& acc) {
+    typedef typename LaneTraits<T>::Mask M;
+    const M qpass = vge(o.q, kClamp);
+    // S * d ln S / d a2  =  iR - S * rest,   rest = 2 NH^2/q [q unclamped] + (1-VN^2) zV / 2 + (1-LN^2) zL / 2
+    const T tq = vsel(qpass, (o.NH2 * o.iq) * 2.f, 0.f);
+    const T hV = vfma(o.VN2, -0.5f, 0.5f), hL = vfma(o.LN2, -0.5f, 0.5f);
+    const T rest = vfma(hV, o.zV, vfma(hL, o.zL, tq));
+    const T Tk = o.iR - o.S * rest;
+    T gLN0 = LaneTraits<T>::splat(0.f), G = LaneTraits<T>::splat(0.f);
 #pragma unroll
-    for (int j = 0; j < RC; ++j) {
-        const bool qpass = o.q[j] >= kClamp;
-        // d ln S / d a2 * S  =  iR - S * rest,   rest = 2 NH^2/q [q unclamped] + (1-VN^2) zV / 2 + (1-LN^2) zL / 2
-        const float tq = qpass ? 2.f * o.NH2 * o.iq[j] : 0.f;
-        const float rest = fmaf(0.5f * (1.f - o.VN2), o.zV[j], fmaf(0.5f * (1.f - o.LN2), o.zL[j], tq));
-        T[j] = fmaf(-o.S[j], rest, o.iR[j]);
-        G[j] = 0.f;
+    for (int c = 0; c < NC; ++c) {
+        const T gf = AE[c] * o.LN0;
+        gLN0 = vfma(AE[c], o.f[c], gLN0);
+        acc.gd[c] = vfma(gf, 1.f - o.F[c], acc.gd[c]);
+        acc.gs[c] = vfma(gf * o.Smkd[c], g.omp5, acc.gs[c]);
+        const T gfF = gf * o.F[c];
+        acc.ga2[c] = vfma(gfF, Tk, acc.ga2[c]);
+        G = vfma(gfF, o.S, G);                                    // d loss / d ln S
     }
-    float gLN0 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int j = (RC == 1) ? 0 : c;
-        const float AE = A[c] * E[c];
-        const float gf = AE * o.LN0;
-        gLN0 = fmaf(AE, o.f[c], gLN0);
-        acc.gd[c] = fmaf(gf, 1.f - o.F[c], acc.gd[c]);
-        acc.gs[c] = fmaf(gf * o.Smkd[c], g.omp5, acc.gs[c]);
-        const float gfF = gf * o.F[c];
-        acc.ga2[c] = fmaf(gfF, T[j], acc.ga2[c]);
-        G[j] = fmaf(gfF, o.S[j], G[j]);                           // d loss / d ln S
-    }
-    float gNH = 0.f, gVN = 0.f, gLN = 0.f;
-#pragma unroll
-    for (int j = 0; j < RC; ++j) {
-        const bool qpass = o.q[j] >= kClamp;
-        const float cNH = qpass ? 4.f * o.NH * p.oma2[j] * o.iq[j] : 0.f;   // -2 dq/dNH / q
-        const float cVN = fmaf(o.VN, p.oma2[j], o.wV[j]) * o.zV[j];        // -(d ln(VN+wV)/dVN), sign below
-        const float cLN = fmaf(o.LN, p.oma2[j], o.wL[j]) * o.zL[j];
-        gNH = fmaf(G[j], cNH, gNH);
-        gVN = fmaf(-G[j], cVN, gVN);
-        gLN = fmaf(-G[j], cLN, gLN);
-    }
+    const T cNH = vsel(qpass, ((o.NH * p.oma2) * o.iq) * 4.f, 0.f);        // -2 dq/dNH / q
+    const T cVN = vfma(o.VN, p.oma2, o.wV) * o.zV;                          // -d ln(VN+wV)/dVN
+    const T cLN = vfma(o.LN, p.oma2, o.wL) * o.zL;
+    const T gNH = G * cNH, gVN = vneg(G * cVN), gLN = vneg(G * cLN);
     // clamp(min=...) passes the gradient where the raw value is >= the bound (renderers.py:48-52,96)
-    const float gNHr = (o.NHr >= kClamp) ? gNH : 0.f;
-    const float gVNr = (o.VNr >= kClamp) ? gVN : 0.f;
-    const float gLNr = ((o.LNr >= kClamp) ? gLN : 0.f) + ((o.LNr >= 0.f) ? gLN0 : 0.f);
-    const float gh = gNHr * g.ih;                                  // n.h = (n.wi + n.wo) ih
-    const float cw = gh + gVNr, ci = gh + gLNr;
-    acc.gn[0] = fmaf(cw, g.wox, fmaf(ci, g.wix, acc.gn[0]));
-    acc.gn[1] = fmaf(cw, g.woy, fmaf(ci, g.wiy, acc.gn[1]));
-    acc.gn[2] = fmaf(cw, g.woz, fmaf(ci, g.wiz, acc.gn[2]));
+    const T gNHr = vsel(vge(o.NHr, kClamp), gNH, 0.f);
+    const T gVNr = vsel(vge(o.VNr, kClamp), gVN, 0.f);
+    const T gLNr = vsel(vge(o.LNr, kClamp), gLN, 0.f) + vsel(vge(o.LNr, 0.f), gLN0, 0.f);
+    const T gh = gNHr * g.ih;                                      // n.h = (n.wi + n.wo) ih
+    const T cw = gh + gVNr, ci = gh + gLNr;
+    acc.gn[0] = vfma(cw, g.wox, vfma(ci, g.wix, acc.gn[0]));
+    acc.gn[1] = vfma(cw, g.woy, vfma(ci, g.wiy, acc.gn[1]));
+    acc.gn[2] = vfma(cw, g.woz, vfma(ci, g.wiz, acc.gn[2]));
 }
 
-// Turns the accumulators into the 12 API-order gradient channels; `scale` = upstream / element count.
-template <int RC>
-SVB_DEV void acc_to_grad(const Acc& a, const Pix<RC>& p, float scale, float (&out)[12]) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int j = (RC == 1) ? 0 : c;
-        out[c] = a.gn[c] * scale;
-        out[3 + c] = a.gd[c] * (scale * kInvPi);
-        const float r = p.rg[j];
-        out[6 + c] = a.ga2[c] * (4.f * scale) * (r * r * r);       // d a2 / d rough = 4 r^3 [rough >= 1e-3]
-        out[9 + c] = a.gs[c] * scale;
-    }
+// d a2 / d rough = 4 r^3 where the clamp of renderers.py:87 passes gradient (rough >= 1e-3), else 0.
+template <typename T>
+SVB_DEV T rough_chain(T rough) {
+    const T r = vsel(vge(rough, kClamp), rough, 0.f);
+    return ((r * r) * r) * 4.f;
 }
 
 }  // namespace svb

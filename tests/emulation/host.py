@@ -36,32 +36,32 @@ def lin_table(w):
     return torch.linspace(-1, 1, w, dtype=torch.float32).numpy()
 
 
-def loss_forward_backward(inp, tgt, scenes):
+def loss_forward_backward(inp, tgt, scenes, lanes=0):
     inp, tgt, scenes = _f32(inp), _f32(tgt), _f32(scenes)
     B, _, H, W = inp.shape
     grad = np.empty_like(inp)
     lin = lin_table(W)
-    loss = lib().emu_loss_forward_backward(_p(inp), _p(tgt), B, H, W, _p(scenes), scenes.shape[1], _p(lin), _p(grad))
+    loss = lib().emu_loss_forward_backward(_p(inp), _p(tgt), B, H, W, _p(scenes), scenes.shape[1], _p(lin), _p(grad), lanes)
     return loss, grad
 
 
-def render_forward(maps, scenes):
+def render_forward(maps, scenes, lanes=0):
     maps, scenes = _f32(maps), _f32(scenes)
     B, _, H, W = maps.shape
     per_batch = scenes.ndim == 3
     N = scenes.shape[-2]
     out = np.empty((B, N, 3, H, W), dtype=np.float32)
     lin = lin_table(W)
-    lib().emu_render_forward(_p(maps), B, H, W, _p(scenes), N, int(per_batch), _p(lin), _p(out))
+    lib().emu_render_forward(_p(maps), B, H, W, _p(scenes), N, int(per_batch), _p(lin), _p(out), lanes)
     return out
 
 
-def render_backward(maps, scenes, grad_images):
+def render_backward(maps, scenes, grad_images, lanes=0):
     maps, scenes, grad_images = _f32(maps), _f32(scenes), _f32(grad_images)
     B, _, H, W = maps.shape
     per_batch = scenes.ndim == 3
     N = scenes.shape[-2]
     out = np.empty_like(maps)
     lin = lin_table(W)
-    lib().emu_render_backward(_p(maps), B, H, W, _p(scenes), N, int(per_batch), _p(lin), _p(grad_images), _p(out))
+    lib().emu_render_backward(_p(maps), B, H, W, _p(scenes), N, int(per_batch), _p(lin), _p(grad_images), _p(out), lanes)
     return out

@@ -11,19 +11,21 @@ from tests import parity
 from tests.emulation import host as emu
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27"])
-def test_loss_and_gradient_three_way(golden, fixture):
+def test_loss_and_gradient_three_way(golden, fixture, lanes):
     g = golden(fixture)
-    loss, grad = emu.loss_forward_backward(g["input"], g["target"], g["configs"])
+    loss, grad = emu.loss_forward_backward(g["input"], g["target"], g["configs"], lanes)
     parity.check_loss(loss, g["loss_f64"])
     for row in parity.check_grad_groups(grad, g["grad_f32"], g["grad_f64"]):
         print(fixture, row)
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress"])
-def test_renders_three_way(golden, fixture):
+def test_renders_three_way(golden, fixture, lanes):
     g = golden(fixture)
-    got = emu.render_forward(g["input"], g["configs"])
+    got = emu.render_forward(g["input"], g["configs"], lanes)
     print(parity.check_tensor(got, g["renders_f32"], g["renders_f64"], "renders"))
     # the quantity the loss consumes
     dlog = np.abs(np.log(got.astype(np.float64) + 0.1) - np.log(g["renders_f64"] + 0.1)).max()
@@ -38,7 +40,8 @@ def test_render_fixed_scenes(golden):
     parity.check_tensor(got, ref32, ref64, "render_fixed")
 
 
-def test_render_backward_matches_oracle_autograd(golden):
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_render_backward_matches_oracle_autograd(golden, lanes):
     g = golden("loss_stress")
     maps = torch.from_numpy(g["input"]).double().requires_grad_(True)
     cfg = torch.from_numpy(g["configs"])
@@ -47,11 +50,22 @@ def test_render_backward_matches_oracle_autograd(golden):
     (O.render_batch(maps, cfg) * w.double()).sum().backward()
     maps32 = torch.from_numpy(g["input"]).requires_grad_(True)
     (O.render_batch(maps32, cfg) * w).sum().backward()
-    got = emu.render_backward(g["input"], g["configs"], w.numpy())
+    got = emu.render_backward(g["input"], g["configs"], w.numpy(), lanes)
     parity.check_grad_groups(got, maps32.grad.numpy(), maps.grad.numpy(), "render_bwd")
 
 
-def test_identical_maps_give_zero_loss_and_gradient(golden):
-    g = golden("loss_bench")
-    loss, grad = emu.loss_forward_backward(g["input"], g["input"], g["configs"])
-    assert loss == 0.0 and not grad.any()
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress"])
+def test_identical_maps_give_zero_loss_and_gradient(golden, fixture):
+    g = golden(fixture)
+    for lanes in (1, 2):
+        loss, grad = emu.loss_forward_backward(g["input"], g["input"], g["configs"], lanes)
+        assert loss == 0.0 and not grad.any()
+
+
+def test_scalar_and_packed_paths_agree_bitwise(golden):
+    """The F2 lane type performs the same fp32 operations per lane as the scalar path."""
+    g = golden("loss_stress")
+    l1, g1 = emu.loss_forward_backward(g["input"], g["target"], g["configs"], 1)
+    l2, g2 = emu.loss_forward_backward(g["input"], g["target"], g["configs"], 2)
+    np.testing.assert_array_equal(g1, g2)
+    assert abs(l1 - l2) <= 1e-8 * abs(l1)   # lane sums are added in a different order
