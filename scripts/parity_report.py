@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Measured parity of the CUDA path against the reference (golden fixtures) and the oracle (fp32 and
+fp64) - the numbers behind the tolerances in tests/parity.py.  Run on the GPU box:
+    python scripts/parity_report.py > gpurun_out/parity.json
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import svbrdf_estimation_b200 as S                    # noqa: E402
+from oracle import reference_port as O                # noqa: E402
+from tests import parity                               # noqa: E402
+from tests.common import synthetic_maps               # noqa: E402
+
+
+def ours(inp, tgt, cfg):
+    x = torch.as_tensor(inp).cuda().requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, torch.as_tensor(tgt).cuda(), torch.as_tensor(cfg))
+    loss.backward()
+    renders = S.render_records(x.detach(), torch.as_tensor(cfg)).cpu().numpy()
+    return float(loss.detach()), x.grad.cpu().numpy(), renders
+
+
+def report(name, inp, tgt, cfg, l32, g32, r32, l64, g64, r64):
+    loss, grad, renders = ours(inp, tgt, cfg)
+    row = {"case": name, "shape": list(np.shape(inp)), "N": int(np.shape(cfg)[1]),
+           "loss_rel_err_vs_ref64": abs(loss - float(l64)) / abs(float(l64)),
+           "ref32_loss_rel_err_vs_ref64": abs(float(l32) - float(l64)) / abs(float(l64))}
+    for gname, s in parity.GROUPS:
+        row["grad_" + gname] = {"ours_vs_ref32": parity.rel_l2(grad[:, s], g32[:, s]),
+                                "ours_vs_ref64": parity.rel_l2(grad[:, s], g64[:, s]),
+                                "ref32_vs_ref64": parity.rel_l2(g32[:, s], g64[:, s])}
+    if r64 is not None:
+        rel = np.abs(renders - r64) / np.maximum(np.abs(r64), 1e-30)
+        relr = np.abs(r32 - r64) / np.maximum(np.abs(r64), 1e-30)
+        row["renders"] = {"ours_vs_ref32": parity.rel_l2(renders, r32), "ours_vs_ref64": parity.rel_l2(renders, r64),
+                          "ref32_vs_ref64": parity.rel_l2(r32, r64),
+                          "elem_rel_p99.9_ours": float(np.quantile(rel, 0.999)), "elem_rel_p99.9_ref32": float(np.quantile(relr, 0.999)),
+                          "elem_rel_max_ours": float(rel.max()), "elem_rel_max_ref32": float(relr.max()),
+                          "max_abs_dlog_ours": float(np.abs(np.log(renders.astype(np.float64) + 0.1) - np.log(r64 + 0.1)).max()),
+                          "max_abs_dlog_ref32": float(np.abs(np.log(r32.astype(np.float64) + 0.1) - np.log(r64 + 0.1)).max())}
+    return row
+
+
+def main():
+    rows = []
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for fx in ("loss_bench", "loss_stress", "loss_n27"):
+        g = dict(np.load(os.path.join(gdir, fx + ".npz")))
+        rows.append(report("golden:" + fx, g["input"], g["target"], g["configs"], g["loss_f32"], g["grad_f32"],
+                           g.get("renders_f32"), g["loss_f64"], g["grad_f64"], g.get("renders_f64")))
+    for size, batch, stress in ((64, 3, False), (48, 2, True), (128, 4, False), (37, 2, False)):
+        inp, tgt = synthetic_maps(batch, size, 11, stress), synthetic_maps(batch, size, 12, stress)
+        torch.manual_seed(313)
+        cfg = O.sample_loss_configs(batch)
+        l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+        l32, g32 = O.rendering_loss_and_grad(inp, tgt, cfg)
+        r64, r32 = O.render_batch(inp.double(), cfg).numpy(), O.render_batch(inp, cfg).numpy()
+        rows.append(report("oracle:%dx%d B%d%s" % (size, size, batch, " stress" if stress else ""), inp.numpy(), tgt.numpy(),
+                           cfg.numpy(), l32, g32.numpy(), r32, l64, g64.numpy(), r64))
+    print(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -35,7 +35,13 @@ constexpr int kCapLarge = 796;   // records -> 28,656 B
 // threads per CTA by lane type (the packed kernels hold two pixels of state per thread)
 template <typename T> struct Cfg;
 template <> struct Cfg<float> { static constexpr int kThreads = 256; };
-template <> struct Cfg<F2> { static constexpr int kThreads = 128; };
+#ifndef SVB_F2_THREADS
+#define SVB_F2_THREADS 128
+#endif
+template <> struct Cfg<F2> { static constexpr int kThreads = SVB_F2_THREADS; };
+#ifndef SVB_LOSS_MINB
+#define SVB_LOSS_MINB 3   // min CTAs/SM promised to ptxas for the loss kernels (register cap <= 170: measured best)
+#endif
 
 template <int CAP>
 struct SceneBlock {
@@ -91,6 +97,19 @@ __device__ __forceinline__ void store12(float* __restrict__ base, int HW, const 
 __device__ __forceinline__ bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
 __device__ __forceinline__ bool same3(const F2 (&v)[12]) {
     return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
+}
+
+__device__ __forceinline__ bool any_differs(const float (&a)[12], const float (&b)[12]) {
+    bool d = false;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) d = d || (a[c] != b[c]);
+    return d;
+}
+__device__ __forceinline__ B2 any_differs(const F2 (&a)[12], const F2 (&b)[12]) {
+    B2 d = {false, false};
+#pragma unroll
+    for (int c = 0; c < 12; ++c) { d.x = d.x || (lo(a[c]) != lo(b[c])); d.y = d.y || (hi(a[c]) != hi(b[c])); }
+    return d;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -149,16 +168,19 @@ __device__ __forceinline__ T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>
         const Geo<T> g = make_geo<T>(x, y, rec);
         Fwd<T, NC> fi, ft;
         shade_fwd<T, NC, BWD>(g, pi, fi);
-        shade_fwd<T, NC, BWD>(g, pt, ft);   // same arithmetic as the input map: identical maps give exactly 0
+        shade_fwd<T, NC, false>(g, pt, ft);
         T AE[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const T E = g.fall * rec[6 + C0 + c];                          // light colour * falloff
             const T xi = vfma(fi.f[c], E * fi.LN0, kEpsRender);            // radiance + 0.1 (losses.py:46-47)
             const T xt = vfma(ft.f[c], E * ft.LN0, kEpsRender);
-            const T d = vlg2(xi) - vlg2(xt);                               // log2 units; ln2 applied at the end
-            lsum = lsum + vabs(d);
-            if (BWD) AE[c] = vsigned(d, vrcp(xi)) * E;                     // sign(0) = 0 like torch (losses.py:50)
+            // log(xt) - log(xi) as ONE lg2 of the ratio: 1/xi is needed for the gradient anyway.
+            // (log2 units; ln2 is applied once to the reduced loss.)
+            const T ix = vrcp(xi);
+            const T l = vlg2(xt * ix);
+            lsum = lsum + vabs(l);
+            if (BWD) AE[c] = vsigned(l, ix) * (-rec[6 + C0 + c] * g.fall);  // d|l|/dxi = -sign(l)/xi; sign(0) = 0 (losses.py:50)
         }
         if (BWD) shade_bwd<T, NC>(g, pi, fi, AE, acc);
     }
@@ -236,7 +258,7 @@ __device__ __forceinline__ T l1_pixel(const T (&vi)[12], const T (&vt)[12], floa
 }
 
 template <typename T, bool BWD, bool MIXED, int CAP>
-__global__ void __launch_bounds__(Cfg<T>::kThreads)
+__global__ void __launch_bounds__(Cfg<T>::kThreads, SVB_LOSS_MINB)
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
     __shared__ float red[THREADS / 32];
@@ -248,7 +270,16 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
-    const T lsum = loss_pixel<T, BWD>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    // Pixels whose input and target channels are bitwise equal contribute exactly 0 to the loss and to
+    // the gradient, as in the reference (identical renders); the input and the target map go through
+    // differently scheduled instruction sequences here, which would otherwise leave rounding noise.
+    const typename LaneTraits<T>::Mask differs = any_differs(vi, vt);
+    T lsum = loss_pixel<T, BWD>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    lsum = vsel(differs, lsum, 0.f);
+    if (BWD) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) g[c] = vsel(differs, g[c], 0.f);
+    }
     T l1 = LaneTraits<T>::splat(0.f);
     if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
     if (BWD && w.live) store12<T>(a.grad + off, a.HW, g);

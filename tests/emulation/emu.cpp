@@ -18,6 +18,8 @@ inline void ld_lane(const float* p, float& v) { v = p[0]; }
 inline void ld_lane(const float* p, F2& v) { v = mk2(p[0], p[1]); }
 inline void st_lane(float* p, float v) { p[0] = v; }
 inline void st_lane(float* p, F2 v) { p[0] = lo(v); p[1] = hi(v); }
+inline float lane_get(float v, int) { return v; }
+inline float lane_get(F2 v, int j) { return j ? hi(v) : lo(v); }
 inline bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
 inline bool same3(const F2 (&v)[12]) {
     return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
@@ -30,15 +32,16 @@ T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y, const f
         const Geo<T> g = make_geo<T>(x, y, rec);
         Fwd<T, NC> fi, ft;
         shade_fwd<T, NC, true>(g, pi, fi);
-        shade_fwd<T, NC, true>(g, pt, ft);
+        shade_fwd<T, NC, false>(g, pt, ft);
         T AE[NC];
         for (int c = 0; c < NC; ++c) {
             const T E = g.fall * rec[6 + C0 + c];
             const T xi = vfma(fi.f[c], E * fi.LN0, kEpsRender);
             const T xt = vfma(ft.f[c], E * ft.LN0, kEpsRender);
-            const T d = vlg2(xi) - vlg2(xt);
-            lsum = lsum + vabs(d);
-            AE[c] = vsigned(d, vrcp(xi)) * E;
+            const T ix = vrcp(xi);
+            const T l = vlg2(xt * ix);
+            lsum = lsum + vabs(l);
+            AE[c] = vsigned(l, ix) * (-rec[6 + C0 + c] * g.fall);
         }
         shade_bwd<T, NC>(g, pi, fi, AE, acc);
     }
@@ -60,7 +63,7 @@ T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, const fl
 }
 
 template <typename T>
-double loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* rec, int N, float scale, T (&g)[12]) {
+T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* rec, int N, float scale, T (&g)[12]) {
     if (same3(vi) && same3(vt)) {
         const Pix<T, 3> pi = make_pix<T, 3>(&vi[0], &vi[3], &vi[9], vi[6]);
         const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
@@ -74,13 +77,13 @@ double loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const floa
             g[6 + c] = (acc.ga2[c] * scale) * chain;
             g[9 + c] = acc.gs[c] * scale;
         }
-        return hsum(l);
+        return l;
     }
     g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f);
     T l = loss_channel_pass<T, 0>(vi, vt, x, y, rec, N, scale, g);
     l = l + loss_channel_pass<T, 1>(vi, vt, x, y, rec, N, scale, g);
     l = l + loss_channel_pass<T, 2>(vi, vt, x, y, rec, N, scale, g);
-    return hsum(l);
+    return l;
 }
 
 template <typename T>
@@ -92,8 +95,15 @@ double loss_image(const float* input, const float* target, int W, size_t HW, con
         T vi[12], vt[12], g[12], x;
         for (int c = 0; c < 12; ++c) { ld_lane(input + c * HW + p, vi[c]); ld_lane(target + c * HW + p, vt[c]); }
         ld_lane(lin + p % W, x);
-        total += loss_pixel<T>(vi, vt, x, -lin[p / W], rec, N, scale, g);
+        const T l = loss_pixel<T>(vi, vt, x, -lin[p / W], rec, N, scale, g);
         for (int c = 0; c < 12; ++c) st_lane(grad + c * HW + p, g[c]);
+        // bitwise-identical input/target pixels contribute exactly 0 (see loss_kernel)
+        bool differs[2] = {false, false};
+        for (int c = 0; c < 12; ++c)
+            for (int j = 0; j < L; ++j) differs[j] = differs[j] || (input[c * HW + p + j] != target[c * HW + p + j]);
+        for (int j = 0; j < L; ++j)
+            if (!differs[j]) for (int c = 0; c < 12; ++c) grad[c * HW + p + j] = 0.f;
+        for (int j = 0; j < L; ++j) if (differs[j]) total += (double)lane_get(l, j);
     }
     return total;
 }

@@ -164,7 +164,8 @@ def test_upstream_gradient_scaling_and_no_grad(S):
     with torch.no_grad():
         v = S.rendering_loss_with_records(inp, tgt, cfg)
     assert not v.requires_grad
-    assert float(v) == float(S.rendering_loss_with_records(x1.detach(), tgt, cfg))
+    # forward-only and forward+backward kernels are different instruction streams: equal to rounding
+    assert abs(float(v) - float(S.rendering_loss_with_records(x1.detach(), tgt, cfg))) <= 1e-6 * float(v)
     # gradient w.r.t. the target (symmetric loss)
     t = tgt.clone().requires_grad_(True)
     S.rendering_loss_with_records(inp, t, cfg).backward()
