@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsvbrdf_b200.so")
 SOURCES = ["kernels.cu", "host_ctx.cu"]
-HEADERS = [os.path.join(CSRC, "shading.cuh"), os.path.join(CSRC, "internal.h"),
+HEADERS = [os.path.join(CSRC, "shading.cuh"), os.path.join(CSRC, "pixel_ops.cuh"), os.path.join(CSRC, "internal.h"),
            os.path.join(ROOT, "include", "svbrdf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]

@@ -21,27 +21,29 @@
 #include <string.h>
 
 #include "../../include/svbrdf_b200.h"
-#include "shading.cuh"
+#include "pixel_ops.cuh"
 #include "internal.h"
 
 namespace svb {
 
-constexpr int kRecFloats = 9;
 // Kernel parameters may total 32,764 bytes on sm_70+ with CUDA >= 12.1.  Two capacities keep the
 // parameter copy small for the common render(scene, maps) call.
 constexpr int kCapSmall = 64;    // records ->  2,304 B
 constexpr int kCapLarge = 796;   // records -> 28,656 B
 
-// threads per CTA by lane type (the packed kernels hold two pixels of state per thread)
-template <typename T> struct Cfg;
-template <> struct Cfg<float> { static constexpr int kThreads = 256; };
+// Threads per CTA and the occupancy promised to ptxas (register cap) by lane type.  The packed
+// kernels hold two pixels of state per thread; 128 threads x 3 CTAs/SM (<= 170 registers) measured
+// best on B200 (DESIGN.md "Tuning log"): the loop is bound by register-file operand bandwidth, not
+// by occupancy, so more resident warps bought nothing once spills appeared.
 #ifndef SVB_F2_THREADS
 #define SVB_F2_THREADS 128
 #endif
-template <> struct Cfg<F2> { static constexpr int kThreads = SVB_F2_THREADS; };
-#ifndef SVB_LOSS_MINB
-#define SVB_LOSS_MINB 3   // min CTAs/SM promised to ptxas for the loss kernels (register cap <= 170: measured best)
+#ifndef SVB_F2_MINB
+#define SVB_F2_MINB 3
 #endif
+template <typename T> struct Cfg;
+template <> struct Cfg<float> { static constexpr int kThreads = 256; static constexpr int kMinBlocks = 2; };
+template <> struct Cfg<F2> { static constexpr int kThreads = SVB_F2_THREADS; static constexpr int kMinBlocks = SVB_F2_MINB; };
 
 template <int CAP>
 struct SceneBlock {
@@ -94,24 +96,6 @@ __device__ __forceinline__ void store12(float* __restrict__ base, int HW, const 
     for (int c = 0; c < 12; ++c) st_stream(base + (size_t)c * HW, v[c]);
 }
 
-__device__ __forceinline__ bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
-__device__ __forceinline__ bool same3(const F2 (&v)[12]) {
-    return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
-}
-
-__device__ __forceinline__ bool any_differs(const float (&a)[12], const float (&b)[12]) {
-    bool d = false;
-#pragma unroll
-    for (int c = 0; c < 12; ++c) d = d || (a[c] != b[c]);
-    return d;
-}
-__device__ __forceinline__ B2 any_differs(const F2 (&a)[12], const F2 (&b)[12]) {
-    B2 d = {false, false};
-#pragma unroll
-    for (int c = 0; c < 12; ++c) { d.x = d.x || (lo(a[c]) != lo(b[c])); d.y = d.y || (hi(a[c]) != hi(b[c])); }
-    return d;
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -156,109 +140,10 @@ __device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// RenderingLoss / MixedLoss: forward (+ backward) for one thread's pixels over all N records
+// RenderingLoss / MixedLoss kernel (per-pixel work: pixel_ops.cuh)
 // ---------------------------------------------------------------------------------------------
-// C0 = first colour channel of the pass (0 for NC = 3; the pass's channel for NC = 1).
-template <typename T, int NC, int C0, bool BWD>
-__device__ __forceinline__ T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
-                                          const float* __restrict__ rec, int N, Acc<T, NC>& acc) {
-    T lsum = LaneTraits<T>::splat(0.f);
-#pragma unroll 1
-    for (int k = 0; k < N; ++k, rec += kRecFloats) {
-        const Geo<T> g = make_geo<T>(x, y, rec);
-        Fwd<T, NC> fi, ft;
-        shade_fwd<T, NC, BWD>(g, pi, fi);
-        shade_fwd<T, NC, false>(g, pt, ft);
-        T AE[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const T E = g.fall * rec[6 + C0 + c];                          // light colour * falloff
-            const T xi = vfma(fi.f[c], E * fi.LN0, kEpsRender);            // radiance + 0.1 (losses.py:46-47)
-            const T xt = vfma(ft.f[c], E * ft.LN0, kEpsRender);
-            // log(xt) - log(xi) as ONE lg2 of the ratio: 1/xi is needed for the gradient anyway.
-            // (log2 units; ln2 is applied once to the reduced loss.)
-            const T ix = vrcp(xi);
-            const T l = vlg2(xt * ix);
-            lsum = lsum + vabs(l);
-            if (BWD) AE[c] = vsigned(l, ix) * (-rec[6 + C0 + c] * g.fall);  // d|l|/dxi = -sign(l)/xi; sign(0) = 0 (losses.py:50)
-        }
-        if (BWD) shade_bwd<T, NC>(g, pi, fi, AE, acc);
-    }
-    return lsum;
-}
-
-// One single-channel pass (general roughness): channel C of input/target with its own roughness.
-template <typename T, int C, bool BWD>
-__device__ __forceinline__ T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y,
-                                               const float* __restrict__ rec, int N, float scale, T (&g)[12]) {
-    const Pix<T, 1> pi = make_pix<T, 1>(&vi[0], &vi[3 + C], &vi[9 + C], vi[6 + C]);
-    const Pix<T, 1> pt = make_pix<T, 1>(&vt[0], &vt[3 + C], &vt[9 + C], vt[6 + C]);
-    Acc<T, 1> acc;
-    acc_zero(acc);
-    const T l = loss_records<T, 1, C, BWD>(pi, pt, x, y, rec, N, acc);
-    if (BWD) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j] * scale;
-        g[3 + C] = acc.gd[0] * (scale * kInvPi);
-        g[6 + C] = (acc.ga2[0] * scale) * rough_chain(vi[6 + C]);
-        g[9 + C] = acc.gs[0] * scale;
-    }
-    return l;
-}
-
-template <typename T, bool BWD>
-__device__ __forceinline__ T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y,
-                                        const float* __restrict__ rec, int N, float scale, T (&g)[12]) {
-    // fast path: the warp's pixels all carry one roughness value replicated on the three channels
-    if (__all_sync(0xffffffffu, same3(vi) && same3(vt))) {
-        const Pix<T, 3> pi = make_pix<T, 3>(&vi[0], &vi[3], &vi[9], vi[6]);
-        const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
-        Acc<T, 3> acc;
-        acc_zero(acc);
-        const T l = loss_records<T, 3, 0, BWD>(pi, pt, x, y, rec, N, acc);
-        if (BWD) {
-            const T chain = rough_chain(vi[6]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                g[c] = acc.gn[c] * scale;
-                g[3 + c] = acc.gd[c] * (scale * kInvPi);
-                g[6 + c] = (acc.ga2[c] * scale) * chain;
-                g[9 + c] = acc.gs[c] * scale;
-            }
-        }
-        return l;
-    }
-    // general path: three single-channel passes (the loss and all gradients decompose by colour channel)
-    if (BWD) { g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f); }
-    T l = loss_channel_pass<T, 0, BWD>(vi, vt, x, y, rec, N, scale, g);
-    l = l + loss_channel_pass<T, 1, BWD>(vi, vt, x, y, rec, N, scale, g);
-    l = l + loss_channel_pass<T, 2, BWD>(vi, vt, x, y, rec, N, scale, g);
-    return l;
-}
-
-// Map-space L1 terms of SVBRDFL1Loss (losses.py:7-19) for one thread's pixels; adds their gradient.
-template <typename T, bool BWD>
-__device__ __forceinline__ T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]) {
-    T s = LaneTraits<T>::splat(0.f);
-#pragma unroll
-    for (int c = 0; c < 12; ++c) {
-        const bool logged = (c >= 3 && c < 6) || c >= 9;      // diffuse and specular use log(x + 0.01)
-        T d, w = LaneTraits<T>::splat(scale);
-        if (logged) {
-            const T a = vi[c] + kEpsL1, b = vt[c] + kEpsL1;
-            d = (vlg2(a) - vlg2(b)) * kLn2;
-            if (BWD) w = vrcp(a) * scale;
-        } else {
-            d = vi[c] - vt[c];
-        }
-        s = s + vabs(d);
-        if (BWD) g[c] = g[c] + vsigned(d, w);
-    }
-    return s;
-}
-
-template <typename T, bool BWD, bool MIXED, int CAP>
-__global__ void __launch_bounds__(Cfg<T>::kThreads, SVB_LOSS_MINB)
+template <typename T, bool BWD, bool MIXED, bool GREY, int CAP>
+__global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
     __shared__ float red[THREADS / 32];
@@ -270,16 +155,7 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
-    // Pixels whose input and target channels are bitwise equal contribute exactly 0 to the loss and to
-    // the gradient, as in the reference (identical renders); the input and the target map go through
-    // differently scheduled instruction sequences here, which would otherwise leave rounding noise.
-    const typename LaneTraits<T>::Mask differs = any_differs(vi, vt);
-    T lsum = loss_pixel<T, BWD>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
-    lsum = vsel(differs, lsum, 0.f);
-    if (BWD) {
-#pragma unroll
-        for (int c = 0; c < 12; ++c) g[c] = vsel(differs, g[c], 0.f);
-    }
+    const T lsum = loss_pixel<T, BWD, GREY>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
     T l1 = LaneTraits<T>::splat(0.f);
     if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
     if (BWD && w.live) store12<T>(a.grad + off, a.HW, g);
@@ -329,23 +205,12 @@ finalize_kernel(const float* __restrict__ part_render, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// LocalRenderer.render forward / backward
+// LocalRenderer.render forward / backward kernels (per-pixel work: pixel_ops.cuh)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NC, int C0>
-__device__ __forceinline__ void render_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec,
-                                               int N, float* __restrict__ out, int HW, bool live) {
-#pragma unroll 1
-    for (int k = 0; k < N; ++k, rec += kRecFloats, out += (size_t)3 * HW) {
-        const Geo<T> g = make_geo<T>(x, y, rec);
-        Fwd<T, NC> f;
-        shade_fwd<T, NC, false>(g, px, f);
-        if (live) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-                st_stream(out + (size_t)(C0 + c) * HW, f.f[c] * ((g.fall * rec[6 + C0 + c]) * f.LN0));   // renderers.py:100
-        }
-    }
-}
+struct DeviceIO {
+    template <typename T> static __device__ __forceinline__ void ld(const float* p, T& v) { ld_stream(p, v); }
+    template <typename T> static __device__ __forceinline__ void st(float* p, T v) { st_stream(p, v); }
+};
 
 template <typename T, int CAP>
 __global__ void __launch_bounds__(Cfg<T>::kThreads)
@@ -356,46 +221,7 @@ render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
     load12<T>(a.maps + (size_t)b * 12 * a.HW + w.p, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
     float* out = a.images + (size_t)b * a.N * 3 * a.HW + w.p;
-    if (__all_sync(0xffffffffu, same3(v))) {
-        render_records<T, 3, 0>(make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]), w.x, w.y, rec, a.N, out, a.HW, w.live);
-    } else {
-        render_records<T, 1, 0>(make_pix<T, 1>(&v[0], &v[3], &v[9], v[6]), w.x, w.y, rec, a.N, out, a.HW, w.live);
-        render_records<T, 1, 1>(make_pix<T, 1>(&v[0], &v[4], &v[10], v[7]), w.x, w.y, rec, a.N, out, a.HW, w.live);
-        render_records<T, 1, 2>(make_pix<T, 1>(&v[0], &v[5], &v[11], v[8]), w.x, w.y, rec, a.N, out, a.HW, w.live);
-    }
-}
-
-template <typename T, int NC, int C0>
-__device__ __forceinline__ void render_bwd_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec,
-                                                   int N, const float* __restrict__ gin, int HW, Acc<T, NC>& acc) {
-#pragma unroll 1
-    for (int k = 0; k < N; ++k, rec += kRecFloats, gin += (size_t)3 * HW) {
-        const Geo<T> g = make_geo<T>(x, y, rec);
-        T AE[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            T a;
-            ld_stream(gin + (size_t)(C0 + c) * HW, a);
-            AE[c] = a * (g.fall * rec[6 + C0 + c]);
-        }
-        Fwd<T, NC> f;
-        shade_fwd<T, NC, true>(g, px, f);
-        shade_bwd<T, NC>(g, px, f, AE, acc);
-    }
-}
-
-template <typename T, int C>
-__device__ __forceinline__ void render_bwd_channel_pass(const T (&v)[12], T x, float y, const float* __restrict__ rec,
-                                                        int N, const float* __restrict__ gin, int HW, T (&g)[12]) {
-    const Pix<T, 1> px = make_pix<T, 1>(&v[0], &v[3 + C], &v[9 + C], v[6 + C]);
-    Acc<T, 1> acc;
-    acc_zero(acc);
-    render_bwd_records<T, 1, C>(px, x, y, rec, N, gin, HW, acc);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j];
-    g[3 + C] = acc.gd[0] * kInvPi;
-    g[6 + C] = acc.ga2[0] * rough_chain(v[6 + C]);
-    g[9 + C] = acc.gs[0];
+    render_pixel<T, DeviceIO>(v, w.x, w.y, rec, a.N, out, (size_t)a.HW, w.live);
 }
 
 template <typename T, int CAP>
@@ -408,25 +234,7 @@ render_bwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
     load12<T>(a.maps + off, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
     const float* gin = a.gimages + (size_t)b * a.N * 3 * a.HW + w.p;
-    if (__all_sync(0xffffffffu, same3(v))) {
-        const Pix<T, 3> px = make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]);
-        Acc<T, 3> acc;
-        acc_zero(acc);
-        render_bwd_records<T, 3, 0>(px, w.x, w.y, rec, a.N, gin, a.HW, acc);
-        const T chain = rough_chain(v[6]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            g[c] = acc.gn[c];
-            g[3 + c] = acc.gd[c] * kInvPi;
-            g[6 + c] = acc.ga2[c] * chain;
-            g[9 + c] = acc.gs[c];
-        }
-    } else {
-        g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f);
-        render_bwd_channel_pass<T, 0>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
-        render_bwd_channel_pass<T, 1>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
-        render_bwd_channel_pass<T, 2>(v, w.x, w.y, rec, a.N, gin, a.HW, g);
-    }
+    render_bwd_pixel<T, DeviceIO>(v, w.x, w.y, rec, a.N, gin, (size_t)a.HW, g);
     if (w.live) store12<T>(a.gmaps + off, a.HW, g);
 }
 
@@ -540,10 +348,24 @@ static cudaError_t launch_with_scenes(Kernel kernel, dim3 grid, const Args& args
     return cudaGetLastError();
 }
 
+// r == g == b light colour in every record?  (selects the GREY kernels)
+static bool all_grey(const float* recs, int nrec) {
+    for (int i = 0; i < nrec; ++i) {
+        const float* c = recs + (size_t)i * kRecFloats + 6;
+        if (c[0] != c[1] || c[1] != c[2]) return false;
+    }
+    return true;
+}
+
+template <typename T, bool BWD, bool MIXED, bool GREY>
+static cudaError_t launch_loss_g(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, kCapSmall>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, kCapLarge>, grid, a, recs, nrec, st);
+}
 template <typename T, bool BWD, bool MIXED>
 static cudaError_t launch_loss(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, kCapSmall>, grid, a, recs, nrec, st)
-                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, kCapLarge>, grid, a, recs, nrec, st);
+    return all_grey(recs, nrec) ? launch_loss_g<T, BWD, MIXED, true>(small, grid, a, recs, nrec, st)
+                                : launch_loss_g<T, BWD, MIXED, false>(small, grid, a, recs, nrec, st);
 }
 template <typename T>
 static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, const LossArgs& a, const float* recs,

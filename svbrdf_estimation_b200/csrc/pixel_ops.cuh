@@ -1,0 +1,261 @@
+// pixel_ops.cuh - what one thread does with its pixel(s): RenderingLoss / MixedLoss forward (+ backward)
+// and LocalRenderer.render forward / backward over all scene records of a batch element.
+//
+// Shared by the CUDA kernels (kernels.cu) and by the host emulation used in the CPU tests
+// (tests/emulation/emu.cpp, SVB_HOST_EMULATION) so that both run literally the same source.
+// Memory access goes through an IO policy (device: __ldcs/__stcs; host: plain loads/stores).
+//
+// Reference semantics: renderers.py:67-104, losses.py:7-19,29-52 (development/multiImage_pytorch/).
+#pragma once
+#include "shading.cuh"
+
+namespace svb {
+
+constexpr int kRecFloats = 9;   // scene record: camera xyz, light xyz, light colour rgb
+
+#ifdef SVB_HOST_EMULATION
+#define SVB_WARP_ALL(pred) (pred)
+#define SVB_UNROLL1
+#else
+#define SVB_WARP_ALL(pred) __all_sync(0xffffffffu, (pred))
+#define SVB_UNROLL1 _Pragma("unroll 1")
+#endif
+
+// ---- small per-lane predicates ------------------------------------------------------------------------
+SVB_DEV bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; }
+SVB_DEV bool same3(const F2 (&v)[12]) {
+    return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
+}
+// Do the inputs that feed colour channel C (normal, d_C, rough_C, s_C) differ between the two maps?
+template <int C>
+SVB_DEV bool chan_differs(const float (&a)[12], const float (&b)[12]) {
+    return a[0] != b[0] || a[1] != b[1] || a[2] != b[2] || a[3 + C] != b[3 + C] || a[6 + C] != b[6 + C] || a[9 + C] != b[9 + C];
+}
+template <int C>
+SVB_DEV B2 chan_differs(const F2 (&a)[12], const F2 (&b)[12]) {
+    B2 d;
+    d.x = lo(a[0]) != lo(b[0]) || lo(a[1]) != lo(b[1]) || lo(a[2]) != lo(b[2]) || lo(a[3 + C]) != lo(b[3 + C]) ||
+          lo(a[6 + C]) != lo(b[6 + C]) || lo(a[9 + C]) != lo(b[9 + C]);
+    d.y = hi(a[0]) != hi(b[0]) || hi(a[1]) != hi(b[1]) || hi(a[2]) != hi(b[2]) || hi(a[3 + C]) != hi(b[3 + C]) ||
+          hi(a[6 + C]) != hi(b[6 + C]) || hi(a[9 + C]) != hi(b[9 + C]);
+    return d;
+}
+SVB_DEV bool all_or_none(bool a, bool b, bool c) { return (a == b) && (b == c); }
+SVB_DEV bool all_or_none(B2 a, B2 b, B2 c) { return (a.x == b.x) && (b.x == c.x) && (a.y == b.y) && (b.y == c.y); }
+
+// ---------------------------------------------------------------------------------------------
+// RenderingLoss: forward (+ backward) of one thread's pixels over the N records of its batch element
+// ---------------------------------------------------------------------------------------------
+// C0 = first colour channel of the pass (0 for NC = 3; the pass's channel for NC = 1).
+// GREY: every record of the launch has r == g == b light colour (always true for the scenes
+// RenderingLoss samples, environment.py:27,52), so colour * falloff is formed once, not per channel.
+// Returns sum |log2 ratio| (ln2 and the mean are applied to the reduced loss).
+template <typename T, int NC, int C0, bool BWD, bool GREY>
+SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y, const float* __restrict__ rec, int N,
+                       Acc<T, NC>& acc) {
+    T lsum = LaneTraits<T>::splat(0.f);
+    SVB_UNROLL1
+    for (int k = 0; k < N; ++k, rec += kRecFloats) {
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        Fwd<T, NC> fi, ft;
+        shade_fwd<T, NC, BWD>(g, pi, fi);
+        shade_fwd<T, NC, false>(g, pt, ft);
+        T E[NC], ELi[NC], ELt[NC], AE[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (!GREY || c == 0) {
+                E[c] = g.fall * (rec[6 + C0 + c] * kInvPi);               // light colour * falloff / pi
+                ELi[c] = E[c] * fi.LN0; ELt[c] = E[c] * ft.LN0;
+            } else {
+                E[c] = E[0]; ELi[c] = ELi[0]; ELt[c] = ELt[0];
+            }
+            const T xi = vfma(fi.f[c], ELi[c], kEpsRender);                // radiance + 0.1 (losses.py:46-47)
+            const T xt = vfma(ft.f[c], ELt[c], kEpsRender);
+            // log(xt) - log(xi) as ONE lg2 of the ratio: 1/xi is needed for the gradient anyway.
+            const T ix = vrcp(xi);
+            const T l = vlg2(xt * ix);
+            lsum = lsum + vabs(l);
+            // d|l|/d xi = -sign(l)/xi: the accumulators carry +sign(l)/xi and the caller applies the minus
+            // with the final scale.  sign(0) is taken as +1 here: an exact 0 only arises from inputs that
+            // are bitwise identical for this channel, and those are masked in loss_pixel (losses.py:50).
+            if (BWD) AE[c] = vcopysign(ix, l) * E[c];
+        }
+        if (BWD) shade_bwd<T, NC>(g, pi, fi, AE, acc);
+    }
+    return lsum;
+}
+
+// One single-channel pass (general path): channel C of input/target with its own roughness.  `live`
+// masks lanes whose channel-C inputs are bitwise identical (their exact contribution is 0).
+template <typename T, int C, bool BWD, bool GREY>
+SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
+                            float nscale, typename LaneTraits<T>::Mask live, T (&g)[12]) {
+    const Pix<T, 1> pi = make_pix<T, 1>(&vi[0], &vi[3 + C], &vi[9 + C], vi[6 + C]);
+    const Pix<T, 1> pt = make_pix<T, 1>(&vt[0], &vt[3 + C], &vt[9 + C], vt[6 + C]);
+    Acc<T, 1> acc;
+    acc_zero(acc);
+    const T l = loss_records<T, 1, C, BWD, GREY>(pi, pt, x, y, rec, N, acc);
+    if (BWD) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[j] = g[j] + vsel(live, acc.gn[j] * nscale, 0.f);
+        g[3 + C] = vsel(live, acc.gd[0] * nscale, 0.f);
+        g[6 + C] = vsel(live, (acc.ga2[0] * nscale) * rough_chain(vi[6 + C]), 0.f);
+        g[9 + C] = vsel(live, acc.gs[0] * nscale, 0.f);
+    }
+    return vsel(live, l, 0.f);
+}
+
+// Loss (log2 units, unscaled) and d loss / d input (scaled by `scale`) of one thread's pixels.
+//
+// Exact zeros: where the inputs feeding a colour channel are bitwise identical in input and target the
+// reference renders identical values and that channel contributes exactly 0 to the loss and to every
+// gradient.  Here input and target run through differently scheduled instruction sequences, so that
+// case is handled explicitly: the fast path requires that, per pixel, either all three channels differ
+// or none does (fully identical pixels are zeroed at the end); anything else takes the channel-wise path
+// where identical channels are masked.
+template <typename T, bool BWD, bool GREY>
+SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
+                     float scale, T (&g)[12]) {
+    typedef typename LaneTraits<T>::Mask M;
+    const M d0 = chan_differs<0>(vi, vt), d1 = chan_differs<1>(vi, vt), d2 = chan_differs<2>(vi, vt);
+    const float nscale = -scale;    // the accumulators carry the gradient with the opposite sign (loss_records)
+    // fast path: the warp's pixels all carry one roughness value replicated on the three channels
+    if (SVB_WARP_ALL(same3(vi) && same3(vt) && all_or_none(d0, d1, d2))) {
+        const Pix<T, 3> pi = make_pix<T, 3>(&vi[0], &vi[3], &vi[9], vi[6]);
+        const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
+        Acc<T, 3> acc;
+        acc_zero(acc);
+        const T l = loss_records<T, 3, 0, BWD, GREY>(pi, pt, x, y, rec, N, acc);
+        if (BWD) {
+            const T chain = rough_chain(vi[6]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                g[c] = vsel(d0, acc.gn[c] * nscale, 0.f);
+                g[3 + c] = vsel(d0, acc.gd[c] * nscale, 0.f);
+                g[6 + c] = vsel(d0, (acc.ga2[c] * nscale) * chain, 0.f);
+                g[9 + c] = vsel(d0, acc.gs[c] * nscale, 0.f);
+            }
+        }
+        return vsel(d0, l, 0.f);
+    }
+    // general path: three single-channel passes (the loss and all gradients decompose by colour channel)
+    if (BWD) { g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f); }
+    T l = loss_channel_pass<T, 0, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d0, g);
+    l = l + loss_channel_pass<T, 1, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d1, g);
+    l = l + loss_channel_pass<T, 2, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d2, g);
+    return l;
+}
+
+// Map-space L1 terms of SVBRDFL1Loss (losses.py:7-19) for one thread's pixels (natural-log units,
+// unscaled sum); adds their gradient, scaled by `scale`, to g.
+template <typename T, bool BWD>
+SVB_DEV T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]) {
+    T s = LaneTraits<T>::splat(0.f);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+        const bool logged = (c >= 3 && c < 6) || c >= 9;      // diffuse and specular use log(x + 0.01)
+        T d, w = LaneTraits<T>::splat(scale);
+        if (logged) {
+            const T a = vi[c] + kEpsL1, b = vt[c] + kEpsL1;
+            d = (vlg2(a) - vlg2(b)) * kLn2;
+            if (BWD) w = vrcp(a) * scale;
+        } else {
+            d = vi[c] - vt[c];
+        }
+        s = s + vabs(d);
+        if (BWD) g[c] = g[c] + vsigned(d, w);
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LocalRenderer.render forward / backward
+// ---------------------------------------------------------------------------------------------
+// out points at this thread's pixel(s) in images[b,0,0]; records advance by 3*HW floats.
+template <typename T, int NC, int C0, typename IO>
+SVB_DEV void render_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec, int N,
+                            float* __restrict__ out, size_t HW, bool live) {
+    SVB_UNROLL1
+    for (int k = 0; k < N; ++k, rec += kRecFloats, out += 3 * HW) {
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        Fwd<T, NC> f;
+        shade_fwd<T, NC, false>(g, px, f);
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)   // renderers.py:100 (f carries the factor pi)
+                IO::st(out + (size_t)(C0 + c) * HW, f.f[c] * ((g.fall * (rec[6 + C0 + c] * kInvPi)) * f.LN0));
+        }
+    }
+}
+
+template <typename T, typename IO>
+SVB_DEV void render_pixel(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N, float* __restrict__ out,
+                          size_t HW, bool live) {
+    if (SVB_WARP_ALL(same3(v))) {
+        render_records<T, 3, 0, IO>(make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
+    } else {
+        render_records<T, 1, 0, IO>(make_pix<T, 1>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
+        render_records<T, 1, 1, IO>(make_pix<T, 1>(&v[0], &v[4], &v[10], v[7]), x, y, rec, N, out, HW, live);
+        render_records<T, 1, 2, IO>(make_pix<T, 1>(&v[0], &v[5], &v[11], v[8]), x, y, rec, N, out, HW, live);
+    }
+}
+
+template <typename T, int NC, int C0, typename IO>
+SVB_DEV void render_bwd_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec, int N,
+                                const float* __restrict__ gin, size_t HW, Acc<T, NC>& acc) {
+    SVB_UNROLL1
+    for (int k = 0; k < N; ++k, rec += kRecFloats, gin += 3 * HW) {
+        const Geo<T> g = make_geo<T>(x, y, rec);
+        T AE[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            T a;
+            IO::ld(gin + (size_t)(C0 + c) * HW, a);
+            AE[c] = a * (g.fall * (rec[6 + C0 + c] * kInvPi));
+        }
+        Fwd<T, NC> f;
+        shade_fwd<T, NC, true>(g, px, f);
+        shade_bwd<T, NC>(g, px, f, AE, acc);
+    }
+}
+
+template <typename T, int C, typename IO>
+SVB_DEV void render_bwd_channel_pass(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N,
+                                     const float* __restrict__ gin, size_t HW, T (&g)[12]) {
+    const Pix<T, 1> px = make_pix<T, 1>(&v[0], &v[3 + C], &v[9 + C], v[6 + C]);
+    Acc<T, 1> acc;
+    acc_zero(acc);
+    render_bwd_records<T, 1, C, IO>(px, x, y, rec, N, gin, HW, acc);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j];
+    g[3 + C] = acc.gd[0];
+    g[6 + C] = acc.ga2[0] * rough_chain(v[6 + C]);
+    g[9 + C] = acc.gs[0];
+}
+
+// grad_maps of one thread's pixels: sum over records of J^T grad_images (autograd of renderers.py:67-104)
+template <typename T, typename IO>
+SVB_DEV void render_bwd_pixel(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N,
+                              const float* __restrict__ gin, size_t HW, T (&g)[12]) {
+    if (SVB_WARP_ALL(same3(v))) {
+        const Pix<T, 3> px = make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]);
+        Acc<T, 3> acc;
+        acc_zero(acc);
+        render_bwd_records<T, 3, 0, IO>(px, x, y, rec, N, gin, HW, acc);
+        const T chain = rough_chain(v[6]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            g[c] = acc.gn[c];
+            g[3 + c] = acc.gd[c];
+            g[6 + c] = acc.ga2[c] * chain;
+            g[9 + c] = acc.gs[c];
+        }
+    } else {
+        g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f);
+        render_bwd_channel_pass<T, 0, IO>(v, x, y, rec, N, gin, HW, g);
+        render_bwd_channel_pass<T, 1, IO>(v, x, y, rec, N, gin, HW, g);
+        render_bwd_channel_pass<T, 2, IO>(v, x, y, rec, N, gin, HW, g);
+    }
+}
+
+}  // namespace svb

@@ -7,8 +7,7 @@
 //   * everything that does not depend on the maps (wi, wo, |wi+wo|, Fresnel power, light
 //     falloff) is computed once per (pixel, scene record) and shared by the input and the
 //     target map ("Geo");
-//   * the half vector is never formed: n.h = (n.wi + n.wo) / |wi+wo| and
-//     v.h = (1 + wi.wo) / |wi+wo|, |wi+wo|^2 = 2 + 2 wi.wo;
+//   * the half vector is never normalised: n.h = (n.wi + n.wo) / |wi+wo| and v.h = |wi+wo| / 2;
 //   * the Smith term needs no division:  (1 + sqrt(1 + a2 (1-c^2)/c^2)) * c = c + sqrt(c^2 (1-a2) + a2),
 //     so  F G D / (4 VN LN) = F * a2 / (pi q^2 (VN + wV)(LN + wL));
 //   * the xi() Heaviside factors of renderers.py:15-16,27,38 are identically 1 on this path
@@ -109,6 +108,13 @@ SVB_DEV F2 vsel(B2 m, F2 a, float b) { return mk2(m.x ? lo(a) : b, m.y ? hi(a) :
 // sign(d) * v with sign(0) = 0 (torch.sign / l1_loss backward)
 SVB_DEV float vsigned(float d, float v) { return (d > 0.f) ? v : ((d < 0.f) ? -v : 0.f); }
 SVB_DEV F2 vsigned(F2 d, F2 v) { return mk2(vsigned(lo(d), lo(v)), vsigned(hi(d), hi(v))); }
+// |v| with the sign of d (one LOP3 per lane); d == 0 counts as positive - used where an exact zero of d
+// is handled separately (see loss_kernel: bitwise-identical inputs are masked per pixel / per channel)
+SVB_DEV float vcopysign(float v, float d) { return copysignf(v, d); }
+SVB_DEV F2 vcopysign(F2 v, F2 d) { return mk2(copysignf(lo(v), lo(d)), copysignf(hi(v), hi(d))); }
+// (a >= b) ? v : 0 per lane, as a float factor
+SVB_DEV float vstep(float a, float b, float v) { return a >= b ? v : 0.f; }
+SVB_DEV F2 vstep(F2 a, float b, float v) { return mk2(lo(a) >= b ? v : 0.f, hi(a) >= b ? v : 0.f); }
 SVB_DEV float hsum(float a) { return a; }
 SVB_DEV float hsum(F2 a) { return lo(a) + hi(a); }
 
@@ -148,10 +154,13 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
     const T vx = LaneTraits<T>::splat(s[0]) - x;
     const T iv = vrsqrt(vfma(vx, vx, vyz));
     g.wox = vx * iv; g.woy = iv * vy; g.woz = iv * vz;
-    const T c = vfma(g.wix, g.wox, vfma(g.wiy, g.woy, g.wiz * g.woz));
-    const T t = vfma(c, 2.f, 2.f);                          // |wi+wo|^2
-    g.ih = vrsqrt(t);
-    const T vh = vmax((t * g.ih) * 0.5f, kClamp);           // wo.h = (1+c)/|wi+wo|, clamped (renderers.py:49)
+    // |wi+wo| from the summed vector itself (not from 2 + 2 wi.wo): the rounding of the two
+    // normalisations then cancels in n.h to first order exactly where the GGX lobe is sharpest
+    // (mirror configuration, n.wi ~ n.wo), which keeps the fp32 result near the reference's fp64 one.
+    const T hx = g.wix + g.wox, hy = g.wiy + g.woy, hz = g.wiz + g.woz;
+    const T hh = vfma(hx, hx, vfma(hy, hy, hz * hz));
+    g.ih = vrsqrt(hh);
+    const T vh = vmax((hh * g.ih) * 0.5f, kClamp);          // wo.h = |wi+wo|/2 for unit vectors, clamped (renderers.py:49)
     const T m = 1.f - vh, m2 = m * m;
     g.p5 = (m2 * m2) * m;
     g.omp5 = 1.f - g.p5;
@@ -159,10 +168,13 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
 }
 
 // ---- per pixel: quantities of one SVBRDF map that do not depend on the scene record ----------
+// Scaling convention: everything below works with f' = pi * f (BRDF value times pi) so that the
+// diffuse albedo enters unscaled and 1/pi is folded into the light term E' = colour * falloff / pi,
+// which is warp-uniform (one multiply per record instead of per pixel and map).
 template <typename T, int NC>
 struct Pix {
     T nx, ny, nz;      // normal, used as given (not re-normalised; renderers.py:84)
-    T kd[NC];          // diffuse / pi                        (renderers.py:18-20)
+    T d[NC];           // diffuse albedo                      (renderers.py:18-20)
     T s[NC];           // specular albedo
     T a2;              // alpha^2 = clamp(rough,1e-3)^4       (renderers.py:23-24,87)
     T oma2;            // 1 - alpha^2
@@ -174,7 +186,7 @@ SVB_DEV Pix<T, NC> make_pix(const T* n, const T* d, const T* s, T rough) {
     Pix<T, NC> p;
     p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { p.kd[c] = d[c] * kInvPi; p.s[c] = s[c]; }
+    for (int c = 0; c < NC; ++c) { p.d[c] = d[c]; p.s[c] = s[c]; }
     const T r = vmax(rough, kClamp);
     const T a = r * r;
     p.a2 = a * a;
@@ -187,13 +199,13 @@ template <typename T, int NC>
 struct Fwd {
     T NHr, VNr, LNr;       // unclamped dots (for the clamp masks)
     T NH, VN, LN, LN0;
-    T NH2, VN2, LN2;
+    T VN2, LN2;
     T q;                   // GGX denominator before the clamp
     T iq, zV, zL;          // 1/q, 1/(wV (VN+wV)), 1/(wL (LN+wL))
     T wV, wL;
-    T iR;                  // 1 / (pi q^2 (VN+wV)(LN+wL))
-    T S;                   // G D / (4 VN LN)
-    T F[NC], f[NC], Smkd[NC];   // Fresnel, BRDF value, S - kd
+    T iR;                  // 1 / (q^2 (VN+wV)(LN+wL))
+    T S;                   // pi * G D / (4 VN LN) = a2 * iR
+    T F[NC], f[NC], Smd[NC];    // Fresnel, pi * BRDF value, S - d
 };
 
 template <typename T, int NC, bool BWD>
@@ -203,8 +215,8 @@ SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T, NC>& o) {
     o.NHr = (o.LNr + o.VNr) * g.ih;
     o.NH = vmax(o.NHr, kClamp); o.VN = vmax(o.VNr, kClamp); o.LN = vmax(o.LNr, kClamp);
     o.LN0 = vmax(o.LNr, 0.f);                                     // renderers.py:96
-    o.NH2 = o.NH * o.NH; o.VN2 = o.VN * o.VN; o.LN2 = o.LN * o.LN;
-    o.q = 1.f - o.NH2 * p.oma2;                                   // NH^2 a2 + 1 - NH^2 (renderers.py:26)
+    o.VN2 = o.VN * o.VN; o.LN2 = o.LN * o.LN;
+    o.q = 1.f - (o.NH * o.NH) * p.oma2;                           // NH^2 a2 + 1 - NH^2 (renderers.py:26)
     const T qc = vmax(o.q, kClamp);
     const T tV = vfma(o.VN2, p.oma2, p.a2);
     const T tL = vfma(o.LN2, p.oma2, p.a2);
@@ -214,16 +226,16 @@ SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T, NC>& o) {
     if (BWD) {
         const T iq = vrcp(qc), iPV = vrcp(PV), iPL = vrcp(PL);
         o.iq = iq; o.zV = rwV * iPV; o.zL = rwL * iPL;
-        o.iR = ((iq * iq) * (iPV * iPL)) * kInvPi;
+        o.iR = (iq * iq) * (iPV * iPL);
     } else {
-        o.iR = vrcp((qc * qc) * (PV * PL)) * kInvPi;
+        o.iR = vrcp((qc * qc) * (PV * PL));
     }
     o.S = p.a2 * o.iR;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         o.F[c] = vfma(p.s[c], g.omp5, g.p5);                      // s + (1-s)(1-VH)^5 (renderers.py:32)
-        o.Smkd[c] = o.S - p.kd[c];
-        o.f[c] = vfma(o.F[c], o.Smkd[c], p.kd[c]);                // (1-F) kd + F S     (renderers.py:62-65)
+        o.Smd[c] = o.S - p.d[c];
+        o.f[c] = vfma(o.F[c], o.Smd[c], p.d[c]);                  // (1-F) d + F S      (renderers.py:62-65, times pi)
     }
 }
 
@@ -241,40 +253,38 @@ SVB_DEV void acc_zero(Acc<T, NC>& a) {
     for (int c = 0; c < NC; ++c) { a.gd[c] = z; a.gs[c] = z; a.ga2[c] = z; }
 }
 
-// AE[c] = (d loss / d radiance_c) * E_c for this (pixel, record), E_c = light colour_c * falloff.
+// AE[c] = (d loss / d radiance_c) * E'_c for this (pixel, record), E'_c = light colour_c * falloff / pi.
 // Adds the adjoint of shade_fwd and of the radiance product (renderers.py:96-100) into acc.
-// acc.gd is w.r.t. kd = diffuse/pi: the caller multiplies by 1/pi once per pixel.
+// Clamp masks are applied as 0/1 (or 0/2) float factors: one compare-and-set per lane plus a packed
+// multiply is cheaper in register-file cycles than predicated moves of register pairs.
 template <typename T, int NC>
 SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T, NC>& o, const T (&AE)[NC],
                        Acc<T, NC>& acc) {
-    typedef typename LaneTraits<T>::Mask M;
-    const M qpass = vge(o.q, kClamp);
+    // w = 2 NH / q where the clamp on q passes (renderers.py:26), else 0
+    const T w = (o.NH * o.iq) * vstep(o.q, kClamp, 2.f);
     // S * d ln S / d a2  =  iR - S * rest,   rest = 2 NH^2/q [q unclamped] + (1-VN^2) zV / 2 + (1-LN^2) zL / 2
-    const T tq = vsel(qpass, (o.NH2 * o.iq) * 2.f, 0.f);
     const T hV = vfma(o.VN2, -0.5f, 0.5f), hL = vfma(o.LN2, -0.5f, 0.5f);
-    const T rest = vfma(hV, o.zV, vfma(hL, o.zL, tq));
+    const T rest = vfma(o.NH, w, vfma(hV, o.zV, hL * o.zL));
     const T Tk = o.iR - o.S * rest;
-    T gLN0 = LaneTraits<T>::splat(0.f), G = LaneTraits<T>::splat(0.f);
+    T gLN0, G;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const T gf = AE[c] * o.LN0;
-        gLN0 = vfma(AE[c], o.f[c], gLN0);
+        gLN0 = (c == 0) ? AE[c] * o.f[c] : vfma(AE[c], o.f[c], gLN0);
         acc.gd[c] = vfma(gf, 1.f - o.F[c], acc.gd[c]);
-        acc.gs[c] = vfma(gf * o.Smkd[c], g.omp5, acc.gs[c]);
+        acc.gs[c] = vfma(gf * o.Smd[c], g.omp5, acc.gs[c]);
         const T gfF = gf * o.F[c];
         acc.ga2[c] = vfma(gfF, Tk, acc.ga2[c]);
-        G = vfma(gfF, o.S, G);                                    // d loss / d ln S
+        G = (c == 0) ? gfF * o.S : vfma(gfF, o.S, G);             // d loss / d ln S
     }
-    const T cNH = vsel(qpass, ((o.NH * p.oma2) * o.iq) * 4.f, 0.f);        // -2 dq/dNH / q
-    const T cVN = vfma(o.VN, p.oma2, o.wV) * o.zV;                          // -d ln(VN+wV)/dVN
-    const T cLN = vfma(o.LN, p.oma2, o.wL) * o.zL;
-    const T gNH = G * cNH, gVN = vneg(G * cVN), gLN = vneg(G * cLN);
-    // clamp(min=...) passes the gradient where the raw value is >= the bound (renderers.py:48-52,96)
-    const T gNHr = vsel(vge(o.NHr, kClamp), gNH, 0.f);
-    const T gVNr = vsel(vge(o.VNr, kClamp), gVN, 0.f);
-    const T gLNr = vsel(vge(o.LNr, kClamp), gLN, 0.f) + vsel(vge(o.LNr, 0.f), gLN0, 0.f);
+    // d ln S / d NH = 4 NH (1-a2) / q [q unclamped];  d ln S / d VN = -(wV + VN (1-a2)) zV;  same for LN.
+    // clamp(min=...) passes the gradient where the raw value is >= the bound (renderers.py:48-52,96).
+    const T gNHr = (G * (p.oma2 * w)) * vstep(o.NHr, kClamp, 2.f);
+    const T gVNp = (G * (vfma(o.VN, p.oma2, o.wV) * o.zV)) * vstep(o.VNr, kClamp, 1.f);   // = -gVNr
+    const T gLNp = (G * (vfma(o.LN, p.oma2, o.wL) * o.zL)) * vstep(o.LNr, kClamp, 1.f);   // = -gLNr (specular part)
     const T gh = gNHr * g.ih;                                      // n.h = (n.wi + n.wo) ih
-    const T cw = gh + gVNr, ci = gh + gLNr;
+    const T cw = gh - gVNp;
+    const T ci = vfma(gLN0, vstep(o.LNr, 0.f, 1.f), gh - gLNp);
     acc.gn[0] = vfma(cw, g.wox, vfma(ci, g.wix, acc.gn[0]));
     acc.gn[1] = vfma(cw, g.woy, vfma(ci, g.wiy, acc.gn[1]));
     acc.gn[2] = vfma(cw, g.woz, vfma(ci, g.wiz, acc.gn[2]));

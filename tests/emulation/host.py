@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu.cpp")
 LIB = os.path.join(HERE, "libemu.so")
-HDR = os.path.join(HERE, "..", "..", "svbrdf_estimation_b200", "csrc", "shading.cuh")
+HDRS = [os.path.join(HERE, "..", "..", "svbrdf_estimation_b200", "csrc", h) for h in ("shading.cuh", "pixel_ops.cuh")]
 
 _lib = None
 
@@ -16,7 +16,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < max([os.path.getmtime(SRC)] + [os.path.getmtime(h) for h in HDRS]):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", LIB, SRC])
         _lib = ctypes.CDLL(LIB)
         _lib.emu_loss_forward_backward.restype = ctypes.c_double

@@ -235,3 +235,32 @@ def test_ragged_sizes_and_many_records(S):
         loss, grad = ours_loss_and_grad(S, inp.numpy(), tgt.numpy(), cfg.numpy())
         assert abs(loss - float(l64)) <= 5e-6 * float(l64), (size, batch, n)
         assert parity.rel_l2(grad, g64.numpy()) <= 2e-4, (size, batch, n)
+
+
+def test_partially_identical_maps_are_exact(S, golden):
+    """Only diffuse channel 0 differs: channels 1 and 2 render identically in the reference and contribute
+    exactly 0; the kernels take the channel-wise path and mask them."""
+    g = golden("loss_bench")
+    tgt = g["target"].copy()
+    inp = tgt.copy()
+    inp[:, 3] = g["input"][:, 3]
+    cfg = torch.from_numpy(g["configs"])
+    l64, g64 = O.rendering_loss_and_grad(torch.from_numpy(inp).double(), torch.from_numpy(tgt).double(), cfg)
+    loss, grad = ours_loss_and_grad(S, inp, tgt, g["configs"])
+    parity.check_loss(loss, float(l64))
+    for ch in (4, 5, 7, 8, 10, 11):
+        assert not grad[:, ch].any(), ch
+    assert parity.rel_l2(grad, g64.numpy()) <= 1e-4
+
+
+def test_coloured_light_takes_the_general_colour_path(S):
+    """Non-grey light colours (r != g != b) select the non-GREY kernels."""
+    inp, tgt = synthetic_maps(2, 32, 101), synthetic_maps(2, 32, 102)
+    torch.manual_seed(3)
+    cfg = O.sample_loss_configs(2)
+    cfg[..., 6] *= 0.5
+    cfg[..., 8] *= 1.5
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+    loss, grad = ours_loss_and_grad(S, inp.numpy(), tgt.numpy(), cfg.numpy())
+    parity.check_loss(loss, float(l64))
+    assert parity.rel_l2(grad, g64.numpy()) <= 1e-4

@@ -69,3 +69,20 @@ def test_scalar_and_packed_paths_agree_bitwise(golden):
     l2, g2 = emu.loss_forward_backward(g["input"], g["target"], g["configs"], 2)
     np.testing.assert_array_equal(g1, g2)
     assert abs(l1 - l2) <= 1e-8 * abs(l1)   # lane sums are added in a different order
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_partially_identical_maps_are_exact(golden, lanes):
+    """Only diffuse channel 0 differs: the reference renders channels 1 and 2 identically for input and
+    target, so they contribute exactly 0 (losses.py:50 sign(0) = 0); the kernels mask those channels."""
+    g = golden("loss_bench")
+    tgt = g["target"].copy()
+    inp = tgt.copy()
+    inp[:, 3] = g["input"][:, 3]
+    cfg = torch.from_numpy(g["configs"])
+    l64, g64 = O.rendering_loss_and_grad(torch.from_numpy(inp).double(), torch.from_numpy(tgt).double(), cfg)
+    loss, grad = emu.loss_forward_backward(inp, tgt, g["configs"], lanes)
+    parity.check_loss(loss, float(l64))
+    for ch in (4, 5, 7, 8, 10, 11):
+        assert not grad[:, ch].any() and not g64.numpy()[:, ch].any(), ch
+    assert parity.rel_l2(grad, g64.numpy()) <= 1e-4
