@@ -47,8 +47,19 @@ constexpr float kEpsL1 = 0.01f;        // losses.py:13
 
 // ---- scalar MUFU wrappers --------------------------------------------------------------------
 #ifdef SVB_HOST_EMULATION
-SVB_DEV float mufu_rcp(float x) { return 1.0f / x; }
-SVB_DEV float mufu_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#ifdef SVB_EMU_MUFU_NOISE
+// optional model of the MUFU approximation error (pseudo-random, +-SVB_EMU_MUFU_NOISE relative) for
+// sensitivity studies of the algebra on the CPU
+SVB_DEV float mufu_noise(float v) {
+    unsigned b; __builtin_memcpy(&b, &v, 4);
+    b *= 2654435761u;
+    return v * (1.0f + ((float)((b >> 8) & 0xffff) / 32767.5f - 1.0f) * (float)(SVB_EMU_MUFU_NOISE));
+}
+#else
+SVB_DEV float mufu_noise(float v) { return v; }
+#endif
+SVB_DEV float mufu_rcp(float x) { return mufu_noise(1.0f / x); }
+SVB_DEV float mufu_rsqrt(float x) { return mufu_noise(1.0f / sqrtf(x)); }
 SVB_DEV float mufu_lg2(float x) { return log2f(x); }
 #else
 SVB_DEV float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -118,6 +129,14 @@ SVB_DEV F2 vstep(F2 a, float b, float v) { return mk2(lo(a) >= b ? v : 0.f, hi(a
 SVB_DEV float hsum(float a) { return a; }
 SVB_DEV float hsum(F2 a) { return lo(a) + hi(a); }
 
+// rsqrt with one Newton-Raphson step: y (1.5 - 0.5 x y^2); error ~ 1.5 * (MUFU error)^2 + rounding
+template <typename T>
+SVB_DEV T vrsqrt_nr(T x) {
+    const T y = vrsqrt(x);
+    const T e = 1.f - (x * y) * y;
+    return vfma(y * 0.5f, e, y);
+}
+
 template <typename T> struct LaneTraits;
 template <> struct LaneTraits<float> {
     static constexpr int kLanes = 1;
@@ -159,7 +178,7 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
     // (mirror configuration, n.wi ~ n.wo), which keeps the fp32 result near the reference's fp64 one.
     const T hx = g.wix + g.wox, hy = g.wiy + g.woy, hz = g.wiz + g.woz;
     const T hh = vfma(hx, hx, vfma(hy, hy, hz * hz));
-    g.ih = vrsqrt(hh);
+    g.ih = vrsqrt_nr(hh);    // the one MUFU result whose error reaches 1 - (n.h)^2 uncancelled: refine it
     const T vh = vmax((hh * g.ih) * 0.5f, kClamp);          // wo.h = |wi+wo|/2 for unit vectors, clamped (renderers.py:49)
     const T m = 1.f - vh, m2 = m * m;
     g.p5 = (m2 * m2) * m;
