@@ -186,13 +186,13 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 def probe_fp32_peaks(lib, torch, stream):
-    """Measured register-resident FP32 rates (TFLOP/s, FMA = 2) and MUFU rate (T op/s)."""
+    """Measured register-resident FP32 rates in TFLOP/s (FMA = 2): scalar FFMA, packed FFMA2, FMUL+FADD mix."""
     from svbrdf_estimation_b200 import _cabi
     sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     blocks, iters = sms * 16, 4000
     sink = torch.zeros(blocks * 256, device="cuda")
     out = {}
-    for kind, name, flop_per_op in ((0, "ffma", 2.0), (1, "ffma2", 2.0), (2, "mufu_rcp", 1.0), (3, "fmul_fadd", 1.0)):
+    for kind, name, flop_per_op in ((0, "ffma", 2.0), (1, "ffma2", 2.0), (3, "fmul_fadd", 1.0)):
         ops = ctypes.c_int(0)
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
