@@ -55,8 +55,9 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
                        Acc<T, NC>& acc) {
     T lsum = LaneTraits<T>::splat(0.f);
     SVB_UNROLL1
-    for (int k = 0; k < N; ++k, rec += kRecFloats) {
-        const Geo<T> g = make_geo<T>(x, y, rec);
+    for (int k = 0; k < N; ++k) {
+        const float* __restrict__ rk = rec + k * kRecFloats;
+        const Geo<T> g = make_geo<T>(x, y, rk);
         Fwd<T, NC> fi, ft;
         shade_fwd<T, NC, BWD>(g, pi, fi);
         shade_fwd<T, NC, false>(g, pt, ft);
@@ -64,7 +65,7 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (!GREY || c == 0) {
-                E[c] = g.fall * (rec[6 + C0 + c] * kInvPi);               // light colour * falloff / pi
+                E[c] = g.fall * (rk[6 + C0 + c] * kInvPi);                // light colour * falloff / pi
                 ELi[c] = E[c] * fi.LN0; ELt[c] = E[c] * ft.LN0;
             } else {
                 E[c] = E[0]; ELi[c] = ELi[0]; ELt[c] = ELt[0];
@@ -96,11 +97,12 @@ SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, 
     acc_zero(acc);
     const T l = loss_records<T, 1, C, BWD, GREY>(pi, pt, x, y, rec, N, acc);
     if (BWD) {
+        const T ns = vsel(live, LaneTraits<T>::splat(nscale), 0.f);    // masked lanes: scale 0
 #pragma unroll
-        for (int j = 0; j < 3; ++j) g[j] = g[j] + vsel(live, acc.gn[j] * nscale, 0.f);
-        g[3 + C] = vsel(live, acc.gd[0] * nscale, 0.f);
-        g[6 + C] = vsel(live, (acc.ga2[0] * nscale) * rough_chain(vi[6 + C]), 0.f);
-        g[9 + C] = vsel(live, acc.gs[0] * nscale, 0.f);
+        for (int j = 0; j < 3; ++j) g[j] = vfma(acc.gn[j], ns, g[j]);
+        g[3 + C] = acc.gd[0] * ns;
+        g[6 + C] = (acc.ga2[0] * ns) * rough_chain(vi[6 + C]);
+        g[9 + C] = acc.gs[0] * ns;
     }
     return vsel(live, l, 0.f);
 }
@@ -127,13 +129,14 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
         acc_zero(acc);
         const T l = loss_records<T, 3, 0, BWD, GREY>(pi, pt, x, y, rec, N, acc);
         if (BWD) {
-            const T chain = rough_chain(vi[6]);
+            const T ns = vsel(d0, LaneTraits<T>::splat(nscale), 0.f);  // fully identical pixels: scale 0
+            const T chain = rough_chain(vi[6]) * ns;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                g[c] = vsel(d0, acc.gn[c] * nscale, 0.f);
-                g[3 + c] = vsel(d0, acc.gd[c] * nscale, 0.f);
-                g[6 + c] = vsel(d0, (acc.ga2[c] * nscale) * chain, 0.f);
-                g[9 + c] = vsel(d0, acc.gs[c] * nscale, 0.f);
+                g[c] = acc.gn[c] * ns;
+                g[3 + c] = acc.gd[c] * ns;
+                g[6 + c] = acc.ga2[c] * chain;
+                g[9 + c] = acc.gs[c] * ns;
             }
         }
         return vsel(d0, l, 0.f);

@@ -1,0 +1,183 @@
+"""The C ABI called directly (ctypes, raw device pointers) and size-independent properties at the
+BASELINE.json sizes.  Needs a GPU: ``pytest -m gpu``."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import synthetic_maps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from svbrdf_estimation_b200 import _cabi, environment
+    assert torch.cuda.is_available()
+    return _cabi.lib(), _cabi, environment
+
+
+def device_loss(lib, _cabi, inp, tgt, rec, grad=True, mixed=None):
+    B, _, H, W = inp.shape
+    N = rec.shape[1]
+    lin = torch.linspace(-1, 1, W, device=inp.device)
+    nbytes = lib.svbrdf_b200_workspace_bytes(B, N, H, W)
+    ws = torch.empty(nbytes // 4 + 1, device=inp.device)
+    out = torch.zeros(3, device=inp.device)
+    g = torch.empty_like(inp) if grad else None
+    st = torch.cuda.current_stream().cuda_stream
+    if mixed is not None:
+        _cabi.check(lib.svbrdf_b200_mixed_loss_forward_backward(inp.data_ptr(), tgt.data_ptr(), B, H, W, rec.data_ptr(), N,
+                                                                float(mixed), lin.data_ptr(), out.data_ptr(),
+                                                                g.data_ptr() if grad else None, ws.data_ptr(), nbytes, st))
+    elif grad:
+        _cabi.check(lib.svbrdf_b200_loss_forward_backward(inp.data_ptr(), tgt.data_ptr(), B, H, W, rec.data_ptr(), N,
+                                                          lin.data_ptr(), out.data_ptr(), g.data_ptr(), ws.data_ptr(), nbytes, st))
+    else:
+        _cabi.check(lib.svbrdf_b200_loss_forward(inp.data_ptr(), tgt.data_ptr(), B, H, W, rec.data_ptr(), N,
+                                                 lin.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, st))
+    torch.cuda.synchronize()
+    return out.cpu(), g
+
+
+def test_status_codes_on_device(env):
+    lib, _cabi, E = env
+    inp = synthetic_maps(1, 8, 1).cuda()
+    rec = E.sample_loss_configs(1)
+    lin = torch.linspace(-1, 1, 8, device="cuda")
+    out = torch.zeros(1, device="cuda")
+    ws = torch.empty(64, device="cuda")
+    st = lib.svbrdf_b200_loss_forward(inp.data_ptr(), inp.data_ptr(), 1, 8, 8, rec.data_ptr(), 9, lin.data_ptr(),
+                                      out.data_ptr(), ws.data_ptr(), 4, None)
+    assert st == _cabi.E_INVALID and b"workspace" in lib.svbrdf_b200_last_error()
+    st = lib.svbrdf_b200_loss_forward_backward(inp.data_ptr(), inp.data_ptr(), 1, 8, 8, rec.data_ptr(), 9, lin.data_ptr(),
+                                               out.data_ptr(), None, ws.data_ptr(), 256, None)
+    assert st == _cabi.E_INVALID
+    st = lib.svbrdf_b200_scale_grad(None, 10, out.data_ptr(), None)
+    assert st == _cabi.E_INVALID
+    assert lib.svbrdf_b200_scale_grad(out.data_ptr(), 0, out.data_ptr(), None) == 0
+
+
+def test_forward_only_forward_backward_and_mixed_agree(env):
+    lib, _cabi, E = env
+    inp, tgt = synthetic_maps(3, 40, 1).cuda(), synthetic_maps(3, 40, 2).cuda()
+    torch.manual_seed(1)
+    rec = E.sample_loss_configs(3)
+    o_f, _ = device_loss(lib, _cabi, inp, tgt, rec, grad=False)
+    o_b, g_b = device_loss(lib, _cabi, inp, tgt, rec, grad=True)
+    o_m, g_m = device_loss(lib, _cabi, inp, tgt, rec, grad=True, mixed=0.1)
+    o_m0, g_m0 = device_loss(lib, _cabi, inp, tgt, rec, grad=True, mixed=0.0)
+    assert abs(float(o_f[0]) - float(o_b[0])) <= 1e-6 * float(o_b[0])
+    assert abs(float(o_m[1]) - float(o_b[0])) <= 1e-6 * float(o_b[0])
+    assert abs(float(o_m[0]) - (float(o_m[1]) + 0.1 * float(o_m[2]))) <= 1e-6 * float(o_m[0])
+    torch.testing.assert_close(g_m0, g_b, rtol=1e-5, atol=1e-12)
+    # map-L1 part against plain torch ops on the device
+    n0, d0, r0, s0 = inp.split(3, dim=1)
+    n1, d1, r1, s1 = tgt.split(3, dim=1)
+    l1 = torch.nn.functional.l1_loss
+    want = l1(n0, n1) + l1(torch.log(d0 + 0.01), torch.log(d1 + 0.01)) + l1(r0, r1) + l1(torch.log(s0 + 0.01), torch.log(s1 + 0.01))
+    assert abs(float(o_m[2]) - float(want)) <= 2e-6 * float(want)
+
+
+def test_unaligned_pointers_and_odd_width_take_the_scalar_kernels(env):
+    """W odd -> one pixel per thread kernels; result equals the packed kernels' on an even-width crop."""
+    lib, _cabi, E = env
+    import svbrdf_estimation_b200 as S
+    from oracle import reference_port as O
+    inp, tgt = synthetic_maps(2, 31, 5), synthetic_maps(2, 31, 6)
+    torch.manual_seed(2)
+    rec = E.sample_loss_configs(2)
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), rec)
+    x = inp.cuda().requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, tgt.cuda(), rec)
+    loss.backward()
+    assert abs(float(loss) - float(l64)) <= 2e-6 * float(l64)
+    assert float((x.grad.cpu().double() - g64).norm() / g64.norm()) <= 1e-4
+
+
+@pytest.mark.parametrize("workload", ["c2", "c4"])
+def test_full_size_properties(env, workload):
+    """BASELINE.json sizes (too large for the oracle): determinism, batch-shard additivity, batch
+    permutation equivariance, exact zero for identical maps, symmetry of the loss."""
+    lib, _cabi, E = env
+    B, size, N = (64, 256, 9) if workload == "c2" else (16, 1024, 9)
+    inp, tgt = synthetic_maps(B, size, 11).cuda(), synthetic_maps(B, size, 12).cuda()
+    torch.manual_seed(5)
+    rec = E.sample_loss_configs(B)
+    o1, g1 = device_loss(lib, _cabi, inp, tgt, rec)
+    o2, g2 = device_loss(lib, _cabi, inp, tgt, rec)
+    assert float(o1[0]) == float(o2[0]) and torch.equal(g1, g2)                     # run-to-run deterministic
+    assert torch.isfinite(g1).all() and 0.0 < float(o1[0]) < 10.0
+    # shards: mean of the shard losses = full loss; shard gradients * (b/B) = full gradient slices
+    h = B // 2
+    oa, ga = device_loss(lib, _cabi, inp[:h].contiguous(), tgt[:h].contiguous(), rec[:h].contiguous())
+    ob, gb = device_loss(lib, _cabi, inp[h:].contiguous(), tgt[h:].contiguous(), rec[h:].contiguous())
+    assert abs(0.5 * (float(oa[0]) + float(ob[0])) - float(o1[0])) <= 1e-6 * float(o1[0])
+    torch.testing.assert_close(torch.cat((ga, gb)) * 0.5, g1, rtol=1e-5, atol=1e-14)
+    # permutation of the batch permutes the gradient
+    perm = torch.randperm(B)
+    op, gp = device_loss(lib, _cabi, inp[perm].contiguous(), tgt[perm].contiguous(), rec[perm].contiguous())
+    assert abs(float(op[0]) - float(o1[0])) <= 1e-6 * float(o1[0])
+    assert torch.equal(gp, g1[perm])
+    # identical maps: exactly zero
+    oz, gz = device_loss(lib, _cabi, inp, inp.clone(), rec)
+    assert float(oz[0]) == 0.0 and not bool(gz.any())
+    # the loss is symmetric in (input, target)
+    os_, _ = device_loss(lib, _cabi, tgt, inp, rec, grad=False)
+    assert abs(float(os_[0]) - float(o1[0])) <= 2e-6 * float(o1[0])
+
+
+def test_render_is_linear_in_light_colour_and_falls_off_with_distance(env):
+    import svbrdf_estimation_b200 as S
+    maps = synthetic_maps(2, 64, 3).cuda()
+    base = torch.tensor([[0.2, -0.3, 1.5, -0.4, 0.5, 2.0, 10.0, 20.0, 30.0]])
+    a = S.render_records(maps, base)
+    b = S.render_records(maps, base * torch.tensor([1, 1, 1, 1, 1, 1, 2.0, 2.0, 2.0]))
+    torch.testing.assert_close(b, 2 * a, rtol=2e-6, atol=0)
+    assert (a >= 0).all()
+
+
+def test_host_entry_matches_device_entry(env):
+    lib, _cabi, E = env
+    B, size, N = 6, 64, 9
+    inp, tgt = synthetic_maps(B, size, 21), synthetic_maps(B, size, 22)
+    torch.manual_seed(8)
+    rec = E.sample_loss_configs(B)
+    o, g = device_loss(lib, _cabi, inp.cuda(), tgt.cuda(), rec)
+    ctx = ctypes.c_void_p()
+    _cabi.check(lib.svbrdf_b200_ctx_create(ctypes.byref(ctx), 8, 9, size, size))
+    try:
+        grad = torch.empty_like(inp)
+        loss = ctypes.c_float(0)
+        # pageable host memory
+        _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, inp.data_ptr(), tgt.data_ptr(), B, rec.data_ptr(), N,
+                                                        ctypes.byref(loss), grad.data_ptr()))
+        assert abs(loss.value - float(o[0])) <= 1e-7 * float(o[0])
+        assert torch.equal(grad, g.cpu())          # same kernels, same coordinate table (fill_lin == torch.linspace)
+        # the context's own pinned buffers, forward only
+        n = B * 12 * size * size
+        pin = [lib.svbrdf_b200_ctx_pinned(ctx, w) for w in range(3)]
+        ctypes.memmove(pin[0], inp.data_ptr(), n * 4)
+        ctypes.memmove(pin[1], tgt.data_ptr(), n * 4)
+        _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], B, rec.data_ptr(), N, ctypes.byref(loss), None))
+        assert abs(loss.value - float(o[0])) <= 1e-6 * float(o[0])
+        assert lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], 9, rec.data_ptr(), N, ctypes.byref(loss), None) == _cabi.E_INVALID
+    finally:
+        lib.svbrdf_b200_ctx_destroy(ctx)
+    assert lib.svbrdf_b200_rendering_loss_host(None, inp.data_ptr(), tgt.data_ptr(), B, rec.data_ptr(), N,
+                                               ctypes.byref(loss), None) == _cabi.E_STATE
+
+
+def test_work_is_enqueued_on_the_callers_stream(env):
+    lib, _cabi, E = env
+    import svbrdf_estimation_b200 as S
+    inp, tgt = synthetic_maps(4, 64, 31).cuda(), synthetic_maps(4, 64, 32).cuda()
+    rec = E.sample_loss_configs(4)
+    ref = S.rendering_loss_with_records(inp, tgt, rec)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = S.rendering_loss_with_records(inp, tgt, rec)
+    s.synchronize()
+    assert float(got) == float(ref)
