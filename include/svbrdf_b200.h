@@ -62,6 +62,21 @@ SVBRDF_API const char* svbrdf_b200_last_error(void);
  * scene records per batch element (per-CTA loss partials).  Never 0.                      */
 SVBRDF_API size_t svbrdf_b200_workspace_bytes(int B, int N, int H, int W);
 
+/* Fills lin_host[0..W) with torch.linspace(-1, 1, W) (renderers.py:73), bit-identical to torch's CPU and
+ * CUDA results; upload it once per W and pass it as `lin_dev` below.  Host-only, no CUDA call.       */
+SVBRDF_API int svbrdf_b200_coordinate_table(float* lin_host, int W);
+
+/* ---- scene sampling (environment.py:18-55), host side ---------------------------------------------
+ * Writes records_host[B][n_random + n_specular][9] for batch elements first_batch_element ..
+ * first_batch_element + B - 1: n_random configurations with independently cosine-sampled view and light
+ * directions at unit distance (colour 20) followed by n_specular mirror configurations with
+ * log-normal distances and a common xy shift (colour 50).  Stateless and counter-based: the scenes of
+ * batch element e depend only on (seed, e), so ranks that own different batch slices draw disjoint,
+ * reproducible scenes.  Same distributions as the reference, different random stream (the Python
+ * samplers in environment.py reproduce the reference's torch draws).  Host-only, no CUDA call.       */
+SVBRDF_API int svbrdf_b200_sample_scenes(uint64_t seed, int first_batch_element, int B, int n_random,
+                                         int n_specular, float* records_host);
+
 /* ---- LocalRenderer.render (renderers.py:67-104) ------------------------------------------
  * images[b,k,:,:,:] = radiance of maps[b] under scene record k of batch element b.
  *   scenes_host : [B,N,9] if scenes_per_batch != 0, else [N,9] shared by every b

@@ -20,6 +20,9 @@ PROTOTYPES = {
     "svbrdf_b200_abi_version": (ctypes.c_int, []),
     "svbrdf_b200_last_error": (ctypes.c_char_p, []),
     "svbrdf_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "svbrdf_b200_coordinate_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "svbrdf_b200_sample_scenes": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p]),
     "svbrdf_b200_render_forward": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
                                                   ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_stream]),
     "svbrdf_b200_render_backward": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,

@@ -9,6 +9,8 @@
 // Reference call being replaced: RenderingLoss.forward + loss.backward()
 // (development/multiImage_pytorch/losses.py:29-52, main.py:116-117) on CPU-resident tensors.
 #include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -28,17 +30,75 @@ struct svbrdf_b200_ctx {
 };
 
 // torch.linspace(-1, 1, W) in fp32: step = (end-start)/(W-1); the first half counts up from the
-// start, the second half counts down from the end (ATen RangeFactories), which makes the table
-// antisymmetric.  renderers.py:73.
+// start, the second half counts down from the end (ATen RangeFactories), each as ONE fused
+// multiply-add - which is what both the CPU and the CUDA kernels of torch compute (checked against
+// torch.linspace for W = 2..4096 in tests/test_host_logic.py).  renderers.py:73.
 static void fill_lin(float* lin, int W) {
     if (W == 1) { lin[0] = -1.f; return; }
     const float start = -1.f, end = 1.f;
     const float step = (end - start) / (float)(W - 1);
     const int half = W / 2;
-    for (int i = 0; i < W; ++i) {
-        volatile float prod = (i < half) ? step * (float)i : step * (float)(W - 1 - i);   // no FMA contraction
-        lin[i] = (i < half) ? start + prod : end - prod;
+    for (int i = 0; i < W; ++i)
+        lin[i] = (i < half) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(W - 1 - i), end);
+}
+
+extern "C" int svbrdf_b200_coordinate_table(float* lin_host, int W) {
+    if (!lin_host || W <= 0) return svb_fail(SVBRDF_E_INVALID, "bad coordinate table arguments");
+    fill_lin(lin_host, W);
+    return 0;
+}
+
+// ---- scene sampler (host side) -------------------------------------------------------
+// Counter-based: every draw is a pure function of (seed, batch element, record, draw index), so the
+// call is stateless, thread-safe and independent of B (element b gets the same scenes whatever the
+// batch size or the rank that samples it).  Distributions follow environment.py:18-55 /
+// utils.py:100-111; the stream of numbers is NOT the torch generator's (use the Python samplers for
+// reference-order draws).
+static inline uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline float u01(uint64_t seed, uint64_t b, uint64_t k, uint64_t j) {   // [0,1), 24 random bits
+    const uint64_t h = mix64(mix64(mix64(seed) ^ (b * 0xD1342543DE82EF95ull)) ^ (k << 8 | j));
+    return (float)(h >> 40) * (1.0f / 16777216.0f);
+}
+static inline void hemisphere_dir(float r1, float r2, float* d) {               // utils.py:104-111
+    const float r = sqrtf(r1), phi = 6.283185307179586f * r2;
+    d[0] = r * cosf(phi); d[1] = r * sinf(phi); d[2] = sqrtf(1.0f - r * r);
+}
+static inline float normal01(float u1, float u2) {                              // Box-Muller
+    return sqrtf(-2.0f * logf(1.0f - u1)) * cosf(6.283185307179586f * u2);
+}
+
+extern "C" int svbrdf_b200_sample_scenes(uint64_t seed, int first_batch_element, int B, int n_random, int n_specular,
+                                         float* records_host) {
+    if (!records_host || B <= 0 || n_random < 0 || n_specular < 0 || n_random + n_specular <= 0 || first_batch_element < 0)
+        return svb_fail(SVBRDF_E_INVALID, "bad sampler arguments");
+    const int N = n_random + n_specular;
+    const float lo = 0.001f, hi = 1.0f - 0.1f;                                   // environment.py:20-21,34
+    for (int b = 0; b < B; ++b) {
+        const uint64_t e = (uint64_t)(first_batch_element + b);
+        for (int k = 0; k < N; ++k) {
+            float* r = records_host + ((size_t)b * N + k) * 9;
+            float view[3];
+            hemisphere_dir(lo + (hi - lo) * u01(seed, e, k, 0), u01(seed, e, k, 1), view);
+            if (k < n_random) {                                                  // environment.py:18-30
+                hemisphere_dir(lo + (hi - lo) * u01(seed, e, k, 2), u01(seed, e, k, 3), r + 3);
+                r[0] = view[0]; r[1] = view[1]; r[2] = view[2];
+                r[6] = r[7] = r[8] = 20.0f;
+            } else {                                                             // environment.py:32-55
+                const float dv = expf(0.5f + 0.75f * normal01(u01(seed, e, k, 2), u01(seed, e, k, 3)));
+                const float dl = expf(0.5f + 0.75f * normal01(u01(seed, e, k, 4), u01(seed, e, k, 5)));
+                const float sx = 2.0f * u01(seed, e, k, 6) - 1.0f, sy = 2.0f * u01(seed, e, k, 7) - 1.0f, sz = 0.0001f;
+                r[0] = view[0] * dv + sx;  r[1] = view[1] * dv + sy;  r[2] = view[2] * dv + sz;
+                r[3] = -view[0] * dl + sx; r[4] = -view[1] * dl + sy; r[5] = view[2] * dl + sz;
+                r[6] = r[7] = r[8] = 50.0f;
+            }
+        }
     }
+    return 0;
 }
 
 #define CK(call)                                              \

@@ -148,6 +148,33 @@ def sample_loss_configs_fast(batch, n_random=3, n_specular=6, generator=None):
                       _specular_records(dirs_u(n_specular), log_dist, shift)), dim=1).contiguous()
 
 
+def sample_loss_configs_native(batch, n_random=3, n_specular=6, seed=0, first_batch_element=0):
+    """Scene records from the library's stateless host sampler (``svbrdf_b200_sample_scenes``): the
+    scenes of batch element ``e`` depend only on ``(seed, e)``, which makes sharded runs reproducible
+    regardless of how the batch is split over ranks.  ~50x faster than the reference-order sampler;
+    same distributions, different random stream."""
+    from . import _cabi
+    out = torch.empty(batch, n_random + n_specular, 9, dtype=torch.float32)
+    _cabi.check(_cabi.lib().svbrdf_b200_sample_scenes(int(seed) & (2 ** 64 - 1), int(first_batch_element), int(batch),
+                                                      int(n_random), int(n_specular), out.data_ptr()))
+    return out
+
+
+class NativeSceneSampler:
+    """Callable ``(batch, n_random, n_specular) -> [B,N,9]`` for ``RenderingLoss(renderer, scene_sampler=...)``:
+    fresh scenes on every call (a call counter is mixed into the seed), drawn by the library's host
+    sampler.  ``first_batch_element`` is the global index of this rank's first sample, so that sharded
+    runs draw exactly the scenes an unsharded run would."""
+
+    def __init__(self, seed=313, first_batch_element=0):
+        self.seed, self.first_batch_element, self.calls = int(seed), int(first_batch_element), 0
+
+    def __call__(self, batch, n_random=3, n_specular=6):
+        step_seed = (self.seed * 0x9E3779B97F4A7C15 + self.calls * 0xD1342543DE82EF95) & (2 ** 64 - 1)
+        self.calls += 1
+        return sample_loss_configs_native(batch, n_random, n_specular, step_seed, self.first_batch_element)
+
+
 def generate_random_scenes(count):
     """``count`` Scenes with independently cosine-sampled view and light directions used as
     positions, light colour 20 (environment.py:18-30)."""
@@ -165,4 +192,4 @@ def generate_specular_scenes(count):
 
 __all__ = ["Camera", "Light", "Scene", "generate_random_scenes", "generate_specular_scenes",
            "generate_normalized_random_direction", "pack_scenes", "unpack_scenes", "scene_record",
-           "sample_loss_configs", "sample_loss_configs_fast"]
+           "sample_loss_configs", "sample_loss_configs_fast", "sample_loss_configs_native", "NativeSceneSampler"]

@@ -135,16 +135,19 @@ class RenderingLoss(nn.Module):
     """mean | log(render(input)+0.1) - log(render(target)+0.1) | under freshly sampled light/view
     configurations per batch element (losses.py:21-52).  No parameters, no buffers."""
 
-    def __init__(self, renderer):
+    def __init__(self, renderer, scene_sampler=None):
         super().__init__()
         self.renderer = renderer
         self.random_configuration_count = 3     # losses.py:26
         self.specular_configuration_count = 6   # losses.py:27
+        # None: the reference's sampler (global CPU generator, reference draw order).  Otherwise a
+        # callable (batch, n_random, n_specular) -> [B,N,9], e.g. environment.NativeSceneSampler.
+        self.scene_sampler = scene_sampler
 
     def sample_records(self, batch_size):
-        """[B,N,9] scene records drawn from the global CPU generator in the reference's order."""
-        return env.sample_loss_configs(batch_size, self.random_configuration_count,
-                                       self.specular_configuration_count)
+        """[B,N,9] scene records of one evaluation (fresh scenes per batch element, losses.py:35)."""
+        sampler = self.scene_sampler or env.sample_loss_configs
+        return sampler(batch_size, self.random_configuration_count, self.specular_configuration_count)
 
     def forward(self, input, target):
         if getattr(self.renderer, "fused_rendering_loss", False):
@@ -170,11 +173,11 @@ class MixedLoss(nn.Module):
     builds (main.py:89).  With the fused renderer both terms and their gradient come from one
     kernel pass over the maps."""
 
-    def __init__(self, renderer, l1_weight=0.1):
+    def __init__(self, renderer, l1_weight=0.1, scene_sampler=None):
         super().__init__()
         self.l1_weight = l1_weight
         self.l1_loss = SVBRDFL1Loss()
-        self.rendering_loss = RenderingLoss(renderer)
+        self.rendering_loss = RenderingLoss(renderer, scene_sampler)
 
     def forward(self, input, target):
         rl = self.rendering_loss
