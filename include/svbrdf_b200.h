@@ -124,6 +124,16 @@ SVBRDF_API int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, c
                                             float* grad_input_dev, void* workspace_dev,
                                             size_t workspace_bytes, void* stream);
 
+/* Same, fed by the network's ENCODED output (models.py:334-346 + utils.py:73-98 fused in): encoded_dev is
+ * [B,9,H,W] in [-1,1] after tanh - normal xy, diffuse rgb, roughness, specular rgb.  The kernel decodes
+ * it to the 12-channel maps on the fly (n = normalize(3x,3y,1); (v+1)/2 for diffuse/roughness/specular;
+ * roughness replicated) and writes grad_encoded_dev[B,9,H,W] = d mixed loss / d encoded.             */
+SVBRDF_API int svbrdf_b200_mixed_loss_encoded_forward_backward(const float* encoded_dev, const float* target_dev,
+                                            int B, int H, int W, const float* scenes_host, int N,
+                                            float l1_weight, const float* lin_dev, float* out_dev,
+                                            float* grad_encoded_dev, void* workspace_dev,
+                                            size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer entry point (the call a non-PyTorch caller makes) --------------------------
  * A context owns pinned staging buffers, device buffers and copy/compute streams for problems
  * up to the given size on the current device.                                                */

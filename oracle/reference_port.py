@@ -238,6 +238,21 @@ def mixed_loss(input_maps, target_maps, configs, l1_weight=0.1):
     return l1_weight * maps_l1_loss(input_maps, target_maps) + rendering_loss(input_maps, target_maps, configs)
 
 
+def decode_network_output(encoded):
+    """[...,9,H,W] network output in [-1,1] (normal xy, diffuse, roughness, specular) -> [...,12,H,W] maps.
+    Reference: ``decode_svbrdf`` utils.py:73-88 (normal = normalize(3x, 3y, 1), roughness repeated x3) followed
+    by the [0,1] mapping of diffuse / roughness / specular in ``SingleViewModel.forward`` models.py:340-346
+    (``encode_as_unit_interval`` utils.py:92-93)."""
+    nxy, diffuse, rough, spec = torch.split(encoded, (2, 3, 1, 3), dim=-3)
+    reps = [1] * encoded.dim()
+    reps[-3] = 3
+    rough = rough.repeat(reps)
+    nx, ny = torch.split(nxy.mul(3.0), 1, dim=-3)
+    normals = torch.cat([nx, ny, torch.ones_like(nx)], dim=-3)
+    normals = torch.div(normals, torch.sqrt(torch.sum(torch.pow(normals, 2.0), dim=-3, keepdim=True)))
+    return join_maps(normals, (diffuse + 1) / 2, (rough + 1) / 2, (spec + 1) / 2)
+
+
 def rendering_loss_and_grad(input_maps, target_maps, configs):
     """Convenience for the parity tests: loss value and d loss / d input via autograd
     (what ``loss.backward()`` gives the reference at main.py:116-117)."""

@@ -7,10 +7,10 @@ configuration samplers) and ``utils`` (channel layout, direction sampler).  The 
 """
 from . import environment, losses, renderers, utils
 from .environment import Camera, Light, Scene, generate_random_scenes, generate_specular_scenes
-from .losses import MixedLoss, RenderingLoss, SVBRDFL1Loss, rendering_loss_with_records
+from .losses import MixedLoss, RenderingLoss, SVBRDFL1Loss, mixed_loss_from_encoded, rendering_loss_with_records
 from .renderers import LocalRenderer, render_records
 
 __version__ = "0.1.0"
 __all__ = ["environment", "losses", "renderers", "utils", "Camera", "Light", "Scene",
            "generate_random_scenes", "generate_specular_scenes", "MixedLoss", "RenderingLoss",
-           "SVBRDFL1Loss", "rendering_loss_with_records", "LocalRenderer", "render_records"]
+           "SVBRDFL1Loss", "rendering_loss_with_records", "mixed_loss_from_encoded", "LocalRenderer", "render_records"]

@@ -40,6 +40,10 @@ PROTOTYPES = {
                                                                ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float,
                                                                _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p,
                                                                ctypes.c_size_t, _c_stream]),
+    "svbrdf_b200_mixed_loss_encoded_forward_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                                       ctypes.c_int, _c_float_p, ctypes.c_int,
+                                                                       ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
+                                                                       ctypes.c_void_p, ctypes.c_size_t, _c_stream]),
     "svbrdf_b200_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int]),
     "svbrdf_b200_ctx_destroy": (None, [ctypes.c_void_p]),

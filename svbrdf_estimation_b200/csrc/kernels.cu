@@ -142,23 +142,43 @@ __device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restric
 // ---------------------------------------------------------------------------------------------
 // RenderingLoss / MixedLoss kernel (per-pixel work: pixel_ops.cuh)
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool BWD, bool MIXED, bool GREY, int CAP>
+// ENC: `input` is the network's 9-channel encoded output [B,9,H,W] (decoded on the fly, gradient written
+// for the 9 encoded channels) instead of 12-channel maps.
+template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP>
 __global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
+    constexpr int CIN = ENC ? 9 : 12;
     __shared__ float red[THREADS / 32];
     const int b = blockIdx.y;
     const Where<T> w = locate<T>(a.HW, a.W, a.lin);
     const size_t off = (size_t)b * 12 * a.HW + w.p;
-    T vi[12], vt[12], g[12];
-    load12<T>(a.input + off, a.HW, vi);
+    const size_t off_in = (size_t)b * CIN * a.HW + w.p;
+    T vi[12], vt[12], g[12], inv_len;
+    if (ENC) {
+        T e[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) ld_lane(a.input + off_in + (size_t)c * a.HW, e[c]);
+        decode_encoded<T>(e, vi, inv_len);
+    } else {
+        load12<T>(a.input + off, a.HW, vi);
+    }
     load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
     const T lsum = loss_pixel<T, BWD, GREY>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
     T l1 = LaneTraits<T>::splat(0.f);
     if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
-    if (BWD && w.live) store12<T>(a.grad + off, a.HW, g);
+    if (BWD && w.live) {
+        if (ENC) {
+            T ge[9];
+            encode_grad<T>(vi, inv_len, g, ge);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) st_stream(a.grad + off_in + (size_t)c * a.HW, ge[c]);
+        } else {
+            store12<T>(a.grad + off, a.HW, g);
+        }
+    }
 
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
     const float tr = cta_sum<THREADS>(w.live ? hsum(lsum) : 0.f, red);
@@ -359,8 +379,15 @@ static bool all_grey(const float* recs, int nrec) {
 
 template <typename T, bool BWD, bool MIXED, bool GREY>
 static cudaError_t launch_loss_g(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, kCapSmall>, grid, a, recs, nrec, st)
-                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, kCapLarge>, grid, a, recs, nrec, st);
+    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapSmall>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapLarge>, grid, a, recs, nrec, st);
+}
+// encoded-input variant: always forward+backward, MixedLoss form, large parameter block
+template <typename T>
+static cudaError_t launch_loss_enc(dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    return all_grey(recs, nrec)
+        ? launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, true, true, true, kCapLarge>, grid, a, recs, nrec, st)
+        : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, true, false, true, kCapLarge>, grid, a, recs, nrec, st);
 }
 template <typename T, bool BWD, bool MIXED>
 static cudaError_t launch_loss(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
@@ -380,25 +407,28 @@ static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, co
 // the records do not fit one parameter block).  Pointers are for the WHOLE problem.
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st) {
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded) {
+    const int cin = encoded ? 9 : 12;
     const int cpi = svb_ctas_per_image(HW, W);
     LossArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N;
     a.scale_render = (float)(1.0 / ((double)B * N * 3.0 * HW));
     a.scale_l1 = (float)((double)l1_weight / ((double)B * 3.0 * HW));
-    const bool small = (size_t)bn * N <= (size_t)kCapSmall;
+    const bool small = !encoded && (size_t)bn * N <= (size_t)kCapSmall;
     const int bc_max = batch_per_launch(N, 1, small ? kCapSmall : kCapLarge);
     for (int s0 = b0; s0 < b0 + bn; s0 += bc_max) {
         const int bc = (b0 + bn - s0 < bc_max) ? (b0 + bn - s0) : bc_max;
-        a.input = input + (size_t)s0 * 12 * HW;
+        a.input = input + (size_t)s0 * cin * HW;
         a.target = target + (size_t)s0 * 12 * HW;
-        a.grad = grad ? grad + (size_t)s0 * 12 * HW : nullptr;
+        a.grad = grad ? grad + (size_t)s0 * cin * HW : nullptr;
         a.part_render = part_render + (size_t)s0 * cpi;
         a.part_l1 = part_l1 + (size_t)s0 * cpi;
         const dim3 grid(cpi, bc);
         const float* recs = scenes + (size_t)s0 * N * kRecFloats;
-        const cudaError_t e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st)
-                                            : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st);
+        const cudaError_t e = encoded
+            ? (use_packed(W) ? launch_loss_enc<F2>(grid, a, recs, bc * N, st) : launch_loss_enc<float>(grid, a, recs, bc * N, st))
+            : (use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st)
+                             : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st));
         if (e != cudaSuccess) return cuda_status(e, "loss_kernel launch");
     }
     return 0;
@@ -418,7 +448,7 @@ int svb_launch_finalize(const float* part_render, const float* part_l1, int B, i
 
 static int loss_impl(const float* input, const float* target, int B, int H, int W, const float* scenes, int N,
                      const float* lin, float* out, int n_out, float* grad, void* ws, size_t ws_bytes,
-                     bool mixed, float l1_weight, void* stream) {
+                     bool mixed, float l1_weight, void* stream, bool encoded = false) {
     if (int e = svb_check_shape(B, H, W, N)) return e;
     if (!input || !target || !scenes || !lin || !out || !ws) return fail(SVBRDF_E_INVALID, "null pointer argument");
     if (ws_bytes < svbrdf_b200_workspace_bytes(B, N, H, W)) return fail(SVBRDF_E_INVALID, "workspace too small");
@@ -427,7 +457,7 @@ static int loss_impl(const float* input, const float* target, int B, int H, int 
     float* part_render = (float*)ws;
     float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, W);
     if (int e = svb_launch_loss_range(input, target, grad, B, HW, W, scenes, N, lin, part_render, part_l1, mixed,
-                                      l1_weight, 0, B, st))
+                                      l1_weight, 0, B, st, encoded))
         return e;
     return svb_launch_finalize(part_render, part_l1, B, HW, W, N, mixed, l1_weight, out, n_out, st);
 }
@@ -454,6 +484,16 @@ extern "C" int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, c
                                                        void* workspace_dev, size_t workspace_bytes, void* stream) {
     return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, out_dev, 3, grad_input_dev,
                      workspace_dev, workspace_bytes, true, l1_weight, stream);
+}
+
+extern "C" int svbrdf_b200_mixed_loss_encoded_forward_backward(const float* encoded_dev, const float* target_dev, int B,
+                                                               int H, int W, const float* scenes_host, int N,
+                                                               float l1_weight, const float* lin_dev, float* out_dev,
+                                                               float* grad_encoded_dev, void* workspace_dev,
+                                                               size_t workspace_bytes, void* stream) {
+    if (!grad_encoded_dev) return fail(SVBRDF_E_INVALID, "grad_encoded_dev is null");
+    return loss_impl(encoded_dev, target_dev, B, H, W, scenes_host, N, lin_dev, out_dev, 3, grad_encoded_dev,
+                     workspace_dev, workspace_bytes, true, l1_weight, stream, true);
 }
 
 template <typename T>

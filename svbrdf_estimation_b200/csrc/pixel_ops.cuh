@@ -172,6 +172,40 @@ SVB_DEV T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]
 }
 
 // ---------------------------------------------------------------------------------------------
+// Model-output epilogue: the network emits 9 channels in [-1,1] (after tanh):
+// normal xy, diffuse rgb, roughness, specular rgb (utils.py:52-56).  models.py:334-346 turns them into
+// the 12-channel maps: n = normalize(3 e0, 3 e1, 1) (utils.py:82-86), roughness replicated x3
+// (utils.py:78-80), diffuse / roughness / specular mapped to [0,1] by (x+1)/2 (utils.py:92-93).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+SVB_DEV void decode_encoded(const T (&e)[9], T (&v)[12], T& inv_len) {
+    const T vx = e[0] * 3.f, vy = e[1] * 3.f;
+    const T l2 = vfma(vx, vx, vfma(vy, vy, 1.f));
+    T y = vrsqrt(l2);
+    y = vfma(y * 0.5f, 1.f - (l2 * y) * y, y);          // one Newton step: the reference divides by an exact sqrt
+    inv_len = y;
+    v[0] = vx * y; v[1] = vy * y; v[2] = y;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v[3 + c] = vfma(e[2 + c], 0.5f, 0.5f);
+        v[6 + c] = vfma(e[5], 0.5f, 0.5f);
+        v[9 + c] = vfma(e[6 + c], 0.5f, 0.5f);
+    }
+}
+
+// chain rule of decode_encoded: g[12] = d loss / d maps  ->  ge[9] = d loss / d encoded
+template <typename T>
+SVB_DEV void encode_grad(const T (&v)[12], T inv_len, const T (&g)[12], T (&ge)[9]) {
+    const T ng = vfma(v[0], g[0], vfma(v[1], g[1], v[2] * g[2]));       // n . g_n
+    const T k = inv_len * 3.f;
+    ge[0] = (g[0] - v[0] * ng) * k;                                     // (I - n n^T) g_n / |v|, times d(3e)/de
+    ge[1] = (g[1] - v[1] * ng) * k;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ge[2 + c] = g[3 + c] * 0.5f; ge[6 + c] = g[9 + c] * 0.5f; }
+    ge[5] = ((g[6] + g[7]) + g[8]) * 0.5f;
+}
+
+// ---------------------------------------------------------------------------------------------
 // LocalRenderer.render forward / backward
 // ---------------------------------------------------------------------------------------------
 // out points at this thread's pixel(s) in images[b,0,0]; records advance by 3*HW floats.

@@ -101,6 +101,50 @@ class _FusedLoss(torch.autograd.Function):
         return grad_in, grad_tg, None, None
 
 
+class _FusedEncodedLoss(torch.autograd.Function):
+    """MixedLoss fed by the network's 9-channel encoded output; returns (mixed, rendering, map-L1)."""
+
+    @staticmethod
+    def forward(ctx, encoded, target, records, l1_weight):
+        B, _, H, W = target.shape
+        N = records.shape[1]
+        lib = _cabi.lib()
+        out = torch.empty(3, device=target.device, dtype=torch.float32)
+        ws, ws_bytes = _workspace(B, N, H, W, target.device)
+        lin = coordinate_table(W, target.device)
+        grad = torch.empty_like(encoded)
+        with torch.cuda.device(target.device):
+            _cabi.check(lib.svbrdf_b200_mixed_loss_encoded_forward_backward(
+                encoded.data_ptr(), target.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight),
+                lin.data_ptr(), out.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes,
+                torch.cuda.current_stream().cuda_stream))
+        ctx.grads = (grad, None)
+        ctx.mixed = True
+        return out
+
+    backward = staticmethod(lambda ctx, grad_out: _FusedLoss.backward(ctx, grad_out))
+
+
+def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1):
+    """``MixedLoss`` evaluated directly on the network's encoded output ``[B,9,H,W]`` (after tanh: normal xy,
+    diffuse, roughness, specular in [-1,1]); the decode of models.py:334-346 / utils.py:73-98 and its chain
+    rule run inside the loss kernel.  Returns a 3-vector (mixed, rendering, map-L1); only
+    the first entry is differentiable."""
+    if encoded.dim() != 4 or encoded.shape[1] != 9:
+        raise ValueError("encoded must be [B,9,H,W], got %s" % (tuple(encoded.shape),))
+    if encoded.dtype != torch.float32:
+        raise TypeError("encoded must be float32, got %s" % encoded.dtype)
+    b, _, origin = as_device_maps(target, "target")
+    if tuple(encoded.shape[0:1] + encoded.shape[2:]) != tuple(b.shape[0:1] + b.shape[2:]):
+        raise ValueError("encoded %s and target %s do not match" % (tuple(encoded.shape), tuple(target.shape)))
+    e = (encoded if encoded.is_cuda else encoded.cuda()).contiguous()
+    rec = as_host_records(records, b.shape[0])
+    if rec.dim() != 3:
+        raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
+    out = _FusedEncodedLoss.apply(e, b, rec, float(l1_weight))
+    return out if origin.type == "cuda" else out.to(origin)
+
+
 def _fused_loss(input, target, records, l1_weight):
     _check_pair(input, target)
     a, _, origin = as_device_maps(input, "input")
@@ -187,5 +231,14 @@ class MixedLoss(nn.Module):
             return out[0]
         return self.l1_weight * self.l1_loss(input, target) + rl(input, target)
 
+    def forward_encoded(self, encoded, target):
+        """Same loss on the generator's 9-channel output after tanh (what ``SingleViewModel.forward`` feeds
+        to ``utils.decode_svbrdf``, models.py:334-338): skips materialising the 12-channel prediction."""
+        rl = self.rendering_loss
+        if not getattr(rl.renderer, "fused_rendering_loss", False):
+            from .utils import decode_network_output
+            return self.forward(decode_network_output(encoded), target)
+        return mixed_loss_from_encoded(encoded, target, rl.sample_records(target.shape[0]), float(self.l1_weight))[0]
 
-__all__ = ["SVBRDFL1Loss", "RenderingLoss", "MixedLoss", "rendering_loss_with_records"]
+
+__all__ = ["SVBRDFL1Loss", "RenderingLoss", "MixedLoss", "rendering_loss_with_records", "mixed_loss_from_encoded"]

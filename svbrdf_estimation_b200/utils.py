@@ -25,6 +25,35 @@ def unpack_svbrdf(svbrdf, is_encoded=False):
     return torch.split(svbrdf, sizes, dim=-3)
 
 
+def encode_as_unit_interval(tensor):
+    """[-1,1] -> [0,1] (utils.py:92-93)."""
+    return (tensor + 1) / 2
+
+
+def decode_from_unit_interval(tensor):
+    """[0,1] -> [-1,1] (utils.py:97-98)."""
+    return tensor * 2 - 1
+
+
+def decode_svbrdf(svbrdf):
+    """9-channel network encoding -> 12 channels: normal = normalize(3x, 3y, 1), roughness repeated x3
+    (utils.py:73-88).  Plain torch ops; the fused loss (``MixedLoss.forward_encoded``) does this in-kernel."""
+    nxy, diffuse, roughness, specular = unpack_svbrdf(svbrdf, True)
+    reps = [1] * diffuse.dim()
+    reps[-3] = 3
+    nx, ny = torch.split(nxy.mul(3.0), 1, dim=-3)
+    normals = torch.cat([nx, ny, torch.ones_like(nx)], dim=-3)
+    normals = normals / torch.sqrt(torch.sum(normals * normals, dim=-3, keepdim=True))
+    return pack_svbrdf(normals, diffuse, roughness.repeat(reps), specular)
+
+
+def decode_network_output(encoded):
+    """What ``SingleViewModel.forward`` does after the tanh (models.py:338-346): ``decode_svbrdf`` and the
+    [0,1] mapping of diffuse, roughness and specular."""
+    n, d, r, s = unpack_svbrdf(decode_svbrdf(encoded))
+    return pack_svbrdf(n, encode_as_unit_interval(d), encode_as_unit_interval(r), encode_as_unit_interval(s))
+
+
 def hemisphere_uniforms_to_directions(r1, r2):
     """Cosine-weighted hemisphere direction from two uniforms (utils.py:104-111); any shape, last
     axis of the result is xyz."""

@@ -29,20 +29,41 @@ bool all_grey(const float* recs, int nrec) {
     return true;
 }
 
-template <typename T, bool GREY>
-double loss_image(const float* input, const float* target, int W, size_t HW, const float* rec, int N, const float* lin,
-                  float scale, float* grad) {
+// One image: rendering-loss (+ map-L1 when MIXED) forward+backward.  ENC: `input` is the 9-channel network
+// output, grad has 9 channels.  Returns the unscaled sums (log2 units for the rendering part).
+template <typename T, bool GREY, bool MIXED, bool ENC>
+void loss_image(const float* input, const float* target, int W, size_t HW, const float* rec, int N, const float* lin,
+                float scale_render, float scale_l1, float* grad, double* sum_render, double* sum_l1) {
     constexpr int L = LaneTraits<T>::kLanes;
-    double total = 0.0;
     for (size_t p = 0; p < HW; p += L) {
-        T vi[12], vt[12], g[12], x;
-        for (int c = 0; c < 12; ++c) { HostIO::ld(input + c * HW + p, vi[c]); HostIO::ld(target + c * HW + p, vt[c]); }
+        T vi[12], vt[12], g[12], x, inv_len;
+        if (ENC) {
+            T e[9];
+            for (int c = 0; c < 9; ++c) HostIO::ld(input + c * HW + p, e[c]);
+            decode_encoded<T>(e, vi, inv_len);
+        } else {
+            for (int c = 0; c < 12; ++c) HostIO::ld(input + c * HW + p, vi[c]);
+        }
+        for (int c = 0; c < 12; ++c) HostIO::ld(target + c * HW + p, vt[c]);
         HostIO::ld(lin + p % W, x);
-        const T l = loss_pixel<T, true, GREY>(vi, vt, x, -lin[p / W], rec, N, scale, g);
-        for (int c = 0; c < 12; ++c) HostIO::st(grad + c * HW + p, g[c]);
-        total += (double)hsum(l);
+        const T l = loss_pixel<T, true, GREY>(vi, vt, x, -lin[p / W], rec, N, scale_render, g);
+        *sum_render += (double)hsum(l);
+        if (MIXED) *sum_l1 += (double)hsum(l1_pixel<T, true>(vi, vt, scale_l1, g));
+        if (ENC) {
+            T ge[9];
+            encode_grad<T>(vi, inv_len, g, ge);
+            for (int c = 0; c < 9; ++c) HostIO::st(grad + c * HW + p, ge[c]);
+        } else {
+            for (int c = 0; c < 12; ++c) HostIO::st(grad + c * HW + p, g[c]);
+        }
     }
-    return total;
+}
+
+template <typename T, bool MIXED, bool ENC>
+void loss_image_g(bool grey, const float* input, const float* target, int W, size_t HW, const float* rec, int N,
+                  const float* lin, float sr, float sl, float* grad, double* a, double* b) {
+    if (grey) loss_image<T, true, MIXED, ENC>(input, target, W, HW, rec, N, lin, sr, sl, grad, a, b);
+    else      loss_image<T, false, MIXED, ENC>(input, target, W, HW, rec, N, lin, sr, sl, grad, a, b);
 }
 
 template <typename T>
@@ -73,26 +94,43 @@ void render_bwd_image(const float* maps, int W, size_t HW, const float* rec, int
 
 extern "C" {
 
-// input/target/grad [B,12,H,W]; scenes [B,N,9]; lin [W]; returns the loss (natural log, mean).
+// General entry: input [B,12,H,W] (or [B,9,H,W] when encoded), target [B,12,H,W], scenes [B,N,9], lin [W].
+// mixed: add l1_weight * SVBRDFL1Loss.  out[0] = total, out[1] = rendering loss, out[2] = map-L1 loss.
 // lanes: 0 = choose like the CUDA launcher (2 when W is even), 1 = force scalar, 2 = force packed.
-double emu_loss_forward_backward(const float* input, const float* target, int B, int H, int W, const float* scenes,
-                                 int N, const float* lin, float* grad, int lanes) {
+void emu_loss(const float* input, const float* target, int B, int H, int W, const float* scenes, int N,
+              const float* lin, float* grad, int lanes, int mixed, float l1_weight, int encoded, double* out) {
     const size_t HW = (size_t)H * W;
-    const float scale = (float)(1.0 / ((double)B * N * 3.0 * (double)HW));
+    const float sr = (float)(1.0 / ((double)B * N * 3.0 * (double)HW));
+    const float sl = (float)((double)l1_weight / ((double)B * 3.0 * (double)HW));
     const bool packed = lanes == 2 || (lanes == 0 && (W & 1) == 0);
     const bool grey = all_grey(scenes, B * N);
-    double total = 0.0;
-    for (int b = 0; b < B; ++b) {
-        const size_t off = (size_t)b * 12 * HW;
-        const float* rec = scenes + (size_t)b * N * 9;
-        const float *pi = input + off, *pt = target + off;
-        float* pg = grad + off;
-        if (packed) total += grey ? loss_image<F2, true>(pi, pt, W, HW, rec, N, lin, scale, pg)
-                                  : loss_image<F2, false>(pi, pt, W, HW, rec, N, lin, scale, pg);
-        else        total += grey ? loss_image<float, true>(pi, pt, W, HW, rec, N, lin, scale, pg)
-                                  : loss_image<float, false>(pi, pt, W, HW, rec, N, lin, scale, pg);
+    const int cin = encoded ? 9 : 12;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < B; ++i) {
+        const float* rec = scenes + (size_t)i * N * 9;
+        const float *pi = input + (size_t)i * cin * HW, *pt = target + (size_t)i * 12 * HW;
+        float* pg = grad + (size_t)i * cin * HW;
+        if (packed) {
+            if (encoded)    loss_image_g<F2, true, true>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+            else if (mixed) loss_image_g<F2, true, false>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+            else            loss_image_g<F2, false, false>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+        } else {
+            if (encoded)    loss_image_g<float, true, true>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+            else if (mixed) loss_image_g<float, true, false>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+            else            loss_image_g<float, false, false>(grey, pi, pt, W, HW, rec, N, lin, sr, sl, pg, &a, &b);
+        }
     }
-    return total * (double)kLn2 / ((double)B * N * 3.0 * (double)HW);
+    out[1] = a * (double)kLn2 / ((double)B * N * 3.0 * (double)HW);
+    out[2] = b / ((double)B * 3.0 * (double)HW);
+    out[0] = out[1] + ((mixed || encoded) ? (double)l1_weight * out[2] : 0.0);
+}
+
+// RenderingLoss only (the original entry point of this file).
+double emu_loss_forward_backward(const float* input, const float* target, int B, int H, int W, const float* scenes,
+                                 int N, const float* lin, float* grad, int lanes) {
+    double out[3];
+    emu_loss(input, target, B, H, W, scenes, N, lin, grad, lanes, 0, 0.f, 0, out);
+    return out[1];
 }
 
 // maps [B,12,H,W]; scenes [B,N,9] (per_batch) or [N,9]; images [B,N,3,H,W].

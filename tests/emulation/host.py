@@ -65,3 +65,15 @@ def render_backward(maps, scenes, grad_images, lanes=0):
     lin = lin_table(W)
     lib().emu_render_backward(_p(maps), B, H, W, _p(scenes), N, int(per_batch), _p(lin), _p(grad_images), _p(out), lanes)
     return out
+
+
+def mixed_loss(inp, tgt, scenes, l1_weight=0.1, encoded=False, lanes=0):
+    """-> (total, rendering, map_l1), grad (12 or 9 channels)."""
+    inp, tgt, scenes = _f32(inp), _f32(tgt), _f32(scenes)
+    B, _, H, W = tgt.shape
+    grad = np.empty_like(inp)
+    lin = lin_table(W)
+    out = (ctypes.c_double * 3)()
+    lib().emu_loss(_p(inp), _p(tgt), B, H, W, _p(scenes), scenes.shape[1], _p(lin), _p(grad), lanes, 1,
+                   ctypes.c_float(l1_weight), int(encoded), out)
+    return tuple(out), grad

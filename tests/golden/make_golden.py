@@ -179,6 +179,15 @@ def main():
     np.savez(os.path.join(HERE, "mixed.npz"), loss_f32=val.detach().numpy(), grad_f32=x.grad.numpy(),
              l1_f32=l1.numpy(), seed=np.int64(313))
 
+    # 6. model-output epilogue: decode_svbrdf + [0,1] mapping (utils.py:73-98, models.py:334-346) -------
+    g = torch.Generator("cpu").manual_seed(77)
+    enc = torch.rand(2, 9, 12, 12, generator=g) * 2 - 1
+    dec = ref_utils.decode_svbrdf(enc)
+    n, d, r, s = ref_utils.unpack_svbrdf(dec)
+    dec = ref_utils.pack_svbrdf(n, ref_utils.encode_as_unit_interval(d), ref_utils.encode_as_unit_interval(r),
+                                ref_utils.encode_as_unit_interval(s))
+    np.savez(os.path.join(HERE, "decode.npz"), encoded=enc.numpy(), decoded_f32=dec.numpy())
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-20s %8.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

@@ -264,3 +264,28 @@ def test_coloured_light_takes_the_general_colour_path(S):
     loss, grad = ours_loss_and_grad(S, inp.numpy(), tgt.numpy(), cfg.numpy())
     parity.check_loss(loss, float(l64))
     assert parity.rel_l2(grad, g64.numpy()) <= 1e-4
+
+
+def test_encoded_input_mixed_loss(S, golden):
+    """MixedLoss.forward_encoded: decode of the network output and its chain rule inside the kernel."""
+    gd = golden("decode")
+    enc = torch.from_numpy(gd["encoded"])
+    tgt = torch.from_numpy(golden("loss_bench")["target"][:, :, :12, :12].copy())
+    torch.manual_seed(4)
+    cfg = O.sample_loss_configs(2)
+    e64 = enc.double().requires_grad_(True)
+    want = O.mixed_loss(O.decode_network_output(e64), tgt.double(), cfg, 0.1)
+    want.backward()
+    x = enc.cuda().requires_grad_(True)
+    out = S.mixed_loss_from_encoded(x, tgt.cuda(), cfg, 0.1)
+    out[0].backward()
+    assert abs(float(out[0]) - float(want)) <= 3e-6 * float(want)
+    g64 = e64.grad.numpy()
+    for name, s in (("normal_xy", slice(0, 2)), ("diffuse", slice(2, 5)), ("roughness", slice(5, 6)), ("specular", slice(6, 9))):
+        assert parity.rel_l2(x.grad.cpu().numpy()[:, s], g64[:, s]) <= 1.5e-4, name
+    # module form draws the reference's scenes and equals the decoded 12-channel path
+    torch.manual_seed(9)
+    a = S.MixedLoss(S.LocalRenderer()).forward_encoded(enc.cuda(), tgt.cuda())
+    torch.manual_seed(9)
+    b = S.MixedLoss(S.LocalRenderer())(S.utils.decode_network_output(enc.cuda()), tgt.cuda())
+    assert abs(float(a) - float(b)) <= 3e-6 * float(b)

@@ -86,3 +86,34 @@ def test_partially_identical_maps_are_exact(golden, lanes):
     for ch in (4, 5, 7, 8, 10, 11):
         assert not grad[:, ch].any() and not g64.numpy()[:, ch].any(), ch
     assert parity.rel_l2(grad, g64.numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_mixed_loss_matches_reference(golden, lanes):
+    g, gm = golden("loss_bench"), golden("mixed")
+    torch.manual_seed(int(gm["seed"]))
+    cfg = O.sample_loss_configs(g["input"].shape[0])
+    (total, _, l1), grad = emu.mixed_loss(g["input"], g["target"], cfg.numpy(), 0.1, False, lanes)
+    assert abs(total - float(gm["loss_f32"])) <= 3e-6 * float(gm["loss_f32"])
+    assert abs(l1 - float(gm["l1_f32"])) <= 2e-6 * float(gm["l1_f32"])
+    for name, s in parity.GROUPS:
+        assert parity.rel_l2(grad[:, s], gm["grad_f32"][:, s]) <= 1.5e-4, name
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_encoded_input_loss_and_gradient(golden, lanes):
+    """Model-output epilogue fused into the loss: decode (utils.py:73-98, models.py:340-346) and its chain rule."""
+    gd = golden("decode")
+    enc = torch.from_numpy(gd["encoded"])                      # [2,9,12,12]
+    tgt = torch.from_numpy(golden("loss_bench")["target"][:, :, :12, :12].copy())
+    torch.manual_seed(4)
+    cfg = O.sample_loss_configs(2)
+    e64 = enc.double().requires_grad_(True)
+    want = O.mixed_loss(O.decode_network_output(e64), tgt.double(), cfg, 0.1)
+    want.backward()
+    (total, _, _), grad = emu.mixed_loss(enc.numpy(), tgt.numpy(), cfg.numpy(), 0.1, True, lanes)
+    assert abs(total - float(want)) <= 3e-6 * float(want)
+    assert grad.shape == (2, 9, 12, 12)
+    g64 = e64.grad.numpy()
+    for name, s in (("normal_xy", slice(0, 2)), ("diffuse", slice(2, 5)), ("roughness", slice(5, 6)), ("specular", slice(6, 9))):
+        assert parity.rel_l2(grad[:, s], g64[:, s]) <= 1.5e-4, (name, parity.rel_l2(grad[:, s], g64[:, s]))

@@ -77,3 +77,8 @@ def test_pack_unpack_contract():
     assert torch.equal(O.join_maps(n, d, r, s), maps)
     with pytest.raises(ValueError):
         O.render([0, 0, 1], [0, 0, 1], [1, 1, 1], torch.zeros(12, 4, 6))
+
+
+def test_decode_network_output(golden):
+    g = golden("decode")
+    np.testing.assert_array_equal(O.decode_network_output(t(g["encoded"])).numpy(), g["decoded_f32"])
