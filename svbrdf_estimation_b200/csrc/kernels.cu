@@ -60,8 +60,6 @@ struct LossArgs {
     int HW, W, N;
     float scale_render;    // 1 / (B N 3 H W)
     float scale_l1;        // l1_weight / (B 3 H W)
-    int tiles_per_image;   // tiled (persistent) kernel: ceil(HW / 256)
-    int total_tiles;       // tiled kernel: batch elements of the launch * tiles_per_image
 };
 
 struct RenderArgs {
@@ -188,150 +186,6 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     if (MIXED) {
         const float tl = cta_sum<THREADS>(w.live ? hsum(l1) : 0.f, red);
         if (threadIdx.x == 0) a.part_l1[cta] = tl;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent, bulk-copy-staged variant of loss_kernel for the packed lane type (W even, 16-byte
-// aligned tensors).  grid = min(tiles, SMs * 3); CTA j walks tiles j, j + grid, ...  A tile is 256
-// consecutive pixels of one batch element (128 threads x 2 pixels).  Its 24 (21 when ENC) channel
-// planes are 1 KB contiguous segments: warp 0 issues one cp.async.bulk (TMA 1-D bulk copy) per plane
-// into a 2-stage shared-memory ring, completion is tracked by an mbarrier per stage, and the copy of
-// tile i+2 is issued as soon as the threads have pulled tile i out of its stage - so map loads never
-// stall the shading loop, no thread computes global addresses for loads, and the loss reduction
-// happens once per CTA instead of once per 256 pixels.
-// ---------------------------------------------------------------------------------------------
-constexpr int kTilePix = 2 * Cfg<F2>::kThreads;      // 256
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "SVB_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra SVB_DONE_%=;\n\t"
-        "bra SVB_WAIT_%=;\n\t"
-        "SVB_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <bool ENC>
-__device__ __forceinline__ void tile_issue(const LossArgs& a, int tile, float* stage_smem, unsigned long long* bar) {
-    constexpr int CIN = ENC ? 9 : 12, PLANES = CIN + 12;
-    const int lane = threadIdx.x;                     // called by warp 0 only
-    const int b = tile / a.tiles_per_image, t = tile - b * a.tiles_per_image;
-    const int pix0 = t * kTilePix;
-    const int npix = min(kTilePix, a.HW - pix0);      // multiple of 4 (HW is: W even, H == W)
-    const uint32_t bytes = (uint32_t)npix * 4u;
-    if (lane == 0) mbar_expect_tx(bar, bytes * PLANES);
-    __syncwarp();
-    if (lane < PLANES) {
-        const float* src = (lane < CIN) ? a.input + ((size_t)b * CIN + lane) * a.HW + pix0
-                                        : a.target + ((size_t)b * 12 + (lane - CIN)) * a.HW + pix0;
-        bulk_g2s(stage_smem + lane * kTilePix, src, bytes, bar);
-    }
-}
-
-template <bool BWD, bool MIXED, bool GREY, bool ENC, int CAP>
-__global__ void __launch_bounds__(Cfg<F2>::kThreads, Cfg<F2>::kMinBlocks)
-loss_kernel_tiled(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
-    typedef F2 T;
-    constexpr int THREADS = Cfg<F2>::kThreads;
-    constexpr int CIN = ENC ? 9 : 12, PLANES = CIN + 12;
-    extern __shared__ __align__(128) float stages[];                 // [2][PLANES][kTilePix]
-    __shared__ __align__(8) unsigned long long bar[2];
-    __shared__ float red[THREADS / 32];
-    const int tid = threadIdx.x;
-    const int stride = gridDim.x;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid < 32) {
-        if ((int)blockIdx.x < a.total_tiles) tile_issue<ENC>(a, blockIdx.x, stages, &bar[0]);
-        if ((int)blockIdx.x + stride < a.total_tiles) tile_issue<ENC>(a, blockIdx.x + stride, stages + PLANES * kTilePix, &bar[1]);
-    }
-    T lacc = mk2(0.f, 0.f), l1acc = mk2(0.f, 0.f);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += stride, ++it) {
-        const int st = it & 1;
-        const int b = tile / a.tiles_per_image, t = tile - b * a.tiles_per_image;
-        const int pix = t * kTilePix + 2 * tid;
-        const bool live = pix < a.HW;
-        const int p = live ? pix : a.HW - 2;
-        mbar_wait(&bar[st], (uint32_t)((it >> 1) & 1));
-        // pull this thread's two pixels out of the stage (conflict-free 64-bit shared loads)
-        const float2* sp = reinterpret_cast<const float2*>(stages + st * PLANES * kTilePix) + tid;
-        T vi[12], vt[12], g[12], inv_len;
-        if (live) {
-            if (ENC) {
-                T e[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) { const float2 v = sp[c * (kTilePix / 2)]; e[c] = mk2(v.x, v.y); }
-                decode_encoded<T>(e, vi, inv_len);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) { const float2 v = sp[c * (kTilePix / 2)]; vi[c] = mk2(v.x, v.y); }
-            }
-#pragma unroll
-            for (int c = 0; c < 12; ++c) { const float2 v = sp[(CIN + c) * (kTilePix / 2)]; vt[c] = mk2(v.x, v.y); }
-        } else {                                       // beyond the image: benign values, masked below
-#pragma unroll
-            for (int c = 0; c < 12; ++c) { vi[c] = mk2(0.5f, 0.5f); vt[c] = mk2(0.25f, 0.25f); }
-            inv_len = mk2(1.f, 1.f);
-        }
-        __syncthreads();                               // every thread has read stage `st`
-        if (tid < 32 && tile + 2 * stride < a.total_tiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async writes
-            tile_issue<ENC>(a, tile + 2 * stride, stages + st * PLANES * kTilePix, &bar[st]);
-        }
-        const int row = p / a.W, col = p - row * a.W;
-        T x;
-        ld_lane(a.lin + col, x);
-        const float y = -__ldg(a.lin + row);
-        const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
-
-        const T lsum = loss_pixel<T, BWD, GREY>(vi, vt, x, y, rec, a.N, a.scale_render, g);
-        if (live) lacc = lacc + lsum;
-        if (MIXED) {
-            const T l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
-            if (live) l1acc = l1acc + l1;
-        }
-        if (BWD && live) {
-            if (ENC) {
-                T ge[9];
-                encode_grad<T>(vi, inv_len, g, ge);
-                float* gp = a.grad + (size_t)b * 9 * a.HW + p;
-#pragma unroll
-                for (int c = 0; c < 9; ++c) st_stream(gp + (size_t)c * a.HW, ge[c]);
-            } else {
-                store12<T>(a.grad + (size_t)b * 12 * a.HW + p, a.HW, g);
-            }
-        }
-    }
-    // one partial per CTA; the partial slots of the tiles this CTA also walked are zeroed so that the
-    // finalize kernel can keep summing one slot per tile
-    const float tr = cta_sum<THREADS>(hsum(lacc), red);
-    float tl = 0.f;
-    if (MIXED) tl = cta_sum<THREADS>(hsum(l1acc), red);
-    if (tid == 0 && (int)blockIdx.x < a.total_tiles) {
-        a.part_render[blockIdx.x] = tr;
-        if (MIXED) a.part_l1[blockIdx.x] = tl;
-    }
-    for (int i = blockIdx.x + stride + tid * stride; i < a.total_tiles; i += THREADS * stride) {
-        a.part_render[i] = 0.f;
-        if (MIXED) a.part_l1[i] = 0.f;
     }
 }
 
@@ -528,53 +382,6 @@ static cudaError_t launch_loss_g(bool small, dim3 grid, const LossArgs& a, const
     return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapSmall>, grid, a, recs, nrec, st)
                  : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapLarge>, grid, a, recs, nrec, st);
 }
-// ---- tiled persistent kernels (packed lane type only) ---------------------------------------------------
-#ifndef SVB_PERSISTENT
-#define SVB_PERSISTENT 1
-#endif
-static int sm_count() {
-    static int cached[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (!cached[dev]) {
-        int n = 0;
-        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
-    }
-    return cached[dev];
-}
-template <bool BWD, bool MIXED, bool GREY, bool ENC, int CAP>
-static cudaError_t launch_tiled_k(const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    constexpr int PLANES = (ENC ? 9 : 12) + 12;
-    constexpr size_t kSmem = (size_t)2 * PLANES * kTilePix * sizeof(float);
-    auto kernel = loss_kernel_tiled<BWD, MIXED, GREY, ENC, CAP>;
-    static bool configured = false;      // benign race: the attribute call is idempotent
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const int grid = a.total_tiles < sm_count() * Cfg<F2>::kMinBlocks ? a.total_tiles : sm_count() * Cfg<F2>::kMinBlocks;
-    SceneBlock<CAP> blk;
-    memcpy(blk.v, recs, (size_t)nrec * kRecFloats * sizeof(float));
-    kernel<<<grid, Cfg<F2>::kThreads, kSmem, st>>>(a, blk);
-    return cudaGetLastError();
-}
-template <bool BWD, bool MIXED, bool ENC>
-static cudaError_t launch_tiled_g(bool small, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    const bool grey = all_grey(recs, nrec);
-    if (small) return grey ? launch_tiled_k<BWD, MIXED, true, ENC, kCapSmall>(a, recs, nrec, st)
-                           : launch_tiled_k<BWD, MIXED, false, ENC, kCapSmall>(a, recs, nrec, st);
-    return grey ? launch_tiled_k<BWD, MIXED, true, ENC, kCapLarge>(a, recs, nrec, st)
-                : launch_tiled_k<BWD, MIXED, false, ENC, kCapLarge>(a, recs, nrec, st);
-}
-static cudaError_t launch_tiled(bool bwd, bool mixed, bool encoded, bool small, const LossArgs& a, const float* recs,
-                                int nrec, cudaStream_t st) {
-    if (encoded) return launch_tiled_g<true, true, true>(small, a, recs, nrec, st);
-    if (bwd) return mixed ? launch_tiled_g<true, true, false>(small, a, recs, nrec, st)
-                          : launch_tiled_g<true, false, false>(small, a, recs, nrec, st);
-    return mixed ? launch_tiled_g<false, true, false>(small, a, recs, nrec, st)
-                 : launch_tiled_g<false, false, false>(small, a, recs, nrec, st);
-}
 static inline bool aligned(const void* p, size_t n) { return ((uintptr_t)p & (n - 1)) == 0; }
 
 // encoded-input variant: always forward+backward, MixedLoss form, large parameter block
@@ -622,12 +429,8 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
         a.part_l1 = part_l1 + (size_t)s0 * cpi;
         const dim3 grid(cpi, bc);
         const float* recs = scenes + (size_t)s0 * N * kRecFloats;
-        a.tiles_per_image = cpi;
-        a.total_tiles = bc * cpi;
         cudaError_t e;
-        if (SVB_PERSISTENT && use_packed(W) && aligned(a.input, 16) && aligned(a.target, 16))
-            e = launch_tiled(grad != nullptr, mixed, encoded, (size_t)bc * N <= (size_t)kCapSmall, a, recs, bc * N, st);
-        else if (encoded)
+        if (encoded)
             e = use_packed(W) ? launch_loss_enc<F2>(grid, a, recs, bc * N, st) : launch_loss_enc<float>(grid, a, recs, bc * N, st);
         else
             e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st)
