@@ -7,6 +7,8 @@ same scenes as the reference does.  The CUDA path consumes scenes as packed floa
 ``[.., 9] = (camera xyz, light xyz, light rgb)``; ``sample_loss_configs`` produces a whole
 ``[B, N, 9]`` block for one loss evaluation without building Python objects.
 """
+import math
+
 import numpy as np
 import torch
 
@@ -119,19 +121,88 @@ def _specular_records(view_u, log_dist, shift):
     return torch.cat((cam, light, torch.full_like(cam, SPECULAR_LIGHT_COLOR)), dim=-1)
 
 
+def _affine_like_torch(raw, lo, hi):
+    """What ``tensor.uniform_(lo, hi)`` computes from the raw 24-bit uniform ``raw = uniform_(0, 1)``:
+    ATen evaluates ``x * (to - from) + from`` with x in double, ``to - from`` in float, and rounds once."""
+    lo32, hi32 = np.float32(lo), np.float32(hi)
+    return (raw.double() * float(hi32 - lo32) + float(lo32)).float()
+
+
 def sample_loss_configs(batch, n_random=3, n_specular=6):
     """Scene records of one ``RenderingLoss.forward`` call: for each batch element, ``n_random``
     random then ``n_specular`` mirror configurations (losses.py:34-35) -> [batch, N, 9] float32 CPU.
 
-    The generator is consumed element by element in the reference's order (so a seed reproduces the
-    reference's scenes bit for bit); the trigonometry runs once over the whole block."""
-    ru_v = torch.empty(batch, 2, n_random); ru_l = torch.empty(batch, 2, n_random)
-    su_v = torch.empty(batch, 2, n_specular); s_ld = torch.empty(batch, 2, n_specular)
-    s_sh = torch.empty(batch, n_specular, 2)
+    The global CPU generator is consumed in exactly the reference's order (a seed reproduces the
+    reference's scenes bit for bit, tests/golden/scenes.npz), but with 2-3 generator calls per batch
+    element instead of 9: consecutive ``uniform_`` draws are taken as one raw ``uniform_(0, 1)`` block and
+    mapped to their ranges afterwards, and the two ``normal_`` draws are merged while that keeps ATen on its
+    scalar sampling path (fewer than 16 values).  The trigonometry runs once over the whole block."""
+    nr, ns = int(n_random), int(n_specular)
+    head, tail = 4 * nr + 2 * ns, 2 * ns            # per element: [view/light r1 r2 | spec r1 r2] ... normals ... [shift]
+    if batch <= 0 or nr + ns <= 0:
+        raise ValueError("batch and the number of configurations must be positive")
+    uni = torch.empty(batch, head + tail)
+    nrm = torch.empty(batch, 2, ns)
+    # uniform blocks in stream order: element 0's directions, then (shift of b + directions of b+1), last shift
+    sizes = [head] + [tail + head] * (batch - 1) + [tail]
+    ublocks = uni.view(-1).split(sizes)
+    if 0 < 2 * ns < 16:
+        nblocks = nrm.view(batch, 2 * ns).unbind(0)          # one merged normal_ call per element
+    else:
+        nblocks = nrm.view(2 * batch, ns).unbind(0)          # two calls per element, as in the reference
+    per_elem = len(nblocks) // batch if ns > 0 else 0
+    mean, std = LOG_DISTANCE
+    if head > 0:
+        ublocks[0].uniform_(0.0, 1.0)
     for b in range(batch):
-        _draw_random(ru_v[b], ru_l[b])
-        _draw_specular(su_v[b], s_ld[b], s_sh[b])
-    return torch.cat((_random_records(ru_v, ru_l), _specular_records(su_v, s_ld, s_sh)), dim=1).contiguous()
+        for j in range(per_elem):
+            nblocks[b * per_elem + j].normal_(mean, std)
+        if sizes[b + 1] > 0:
+            ublocks[b + 1].uniform_(0.0, 1.0)
+    plan = _sampler_plan(nr, ns)
+    # every uniform_(lo, hi) of the reference as ATen computes it from the raw draw: x*(hi-lo)+lo with x in
+    # double, (hi-lo) in float, one rounding to float (uniform_real_distribution) - for all columns at once
+    u = (uni.double() * plan["scale"] + plan["offset"]).float()
+    r = torch.sqrt(u.index_select(1, plan["r1"]))                                      # utils.py:104
+    phi = 2 * math.pi * u.index_select(1, plan["r2"])                                  # utils.py:105
+    dirs = torch.stack((r * torch.cos(phi), r * torch.sin(phi), torch.sqrt(1.0 - r ** 2)), dim=-1)   # [B, 2nr+ns, 3]
+    parts = []
+    if nr > 0:
+        parts.append(torch.cat((dirs[:, :nr], dirs[:, nr:2 * nr], plan["col_r"].expand(batch, nr, 3)), dim=-1))
+    if ns > 0:
+        view_s = dirs[:, 2 * nr:]
+        off = torch.cat((u[:, head:].view(batch, ns, 2), plan["z"].expand(batch, ns, 1)), dim=-1)   # environment.py:44
+        dist = torch.exp(nrm)                                                                       # environment.py:38-39
+        cam = view_s * dist[:, 0, :, None] + off                                                    # environment.py:46
+        light = (view_s * plan["mirror"]) * dist[:, 1, :, None] + off                               # environment.py:35,47
+        parts.append(torch.cat((cam, light, plan["col_s"].expand(batch, ns, 3)), dim=-1))
+    return torch.cat(parts, dim=1).contiguous()
+
+
+_PLANS = {}
+
+
+def _sampler_plan(nr, ns):
+    """Column bookkeeping of one batch element's uniform block, cached per (n_random, n_specular)."""
+    key = (nr, ns)
+    plan = _PLANS.get(key)
+    if plan is None:
+        head = 4 * nr + 2 * ns
+        lo32, hi32 = np.float32(0.0 + VIEW_EPS[0]), np.float32(1.0 - VIEW_EPS[1])
+        scale = torch.ones(head + 2 * ns, dtype=torch.float64)
+        offset = torch.zeros(head + 2 * ns, dtype=torch.float64)
+        r1_cols = list(range(0, nr)) + list(range(2 * nr, 3 * nr)) + list(range(4 * nr, 4 * nr + ns))
+        r2_cols = list(range(nr, 2 * nr)) + list(range(3 * nr, 4 * nr)) + list(range(4 * nr + ns, head))
+        scale[r1_cols] = float(hi32 - lo32)
+        offset[r1_cols] = float(lo32)
+        scale[head:] = float(np.float32(1.0) - np.float32(-1.0))
+        offset[head:] = -1.0
+        plan = {"scale": scale, "offset": offset,
+                "r1": torch.tensor(r1_cols, dtype=torch.long), "r2": torch.tensor(r2_cols, dtype=torch.long),
+                "col_r": torch.full((1, 1, 3), RANDOM_LIGHT_COLOR), "col_s": torch.full((1, 1, 3), SPECULAR_LIGHT_COLOR),
+                "z": torch.zeros(1, 1, 1) + 0.0001, "mirror": torch.tensor([-1.0, -1.0, 1.0])}
+        _PLANS[key] = plan
+    return plan
 
 
 def sample_loss_configs_fast(batch, n_random=3, n_specular=6, generator=None):
