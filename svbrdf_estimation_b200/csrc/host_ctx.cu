@@ -2,7 +2,7 @@
 //
 // svbrdf_b200_rendering_loss_host() is the call a caller without device memory makes: maps live
 // in host memory, the loss and d loss / d input come back to host memory.  It is what bench.py
-// times as "e2e".  The batch is cut into slices; slice i's upload (H2D stream), its kernel
+// times as "e2e".  The batch is cut into slices; slice i's uploads (two H2D streams: input, target), its kernel
 // (compute stream) and the download of its gradient (D2H stream) overlap with the neighbouring
 // slices', so the PCIe link - not the kernel - is the bound and both directions are busy at once.
 //
@@ -23,8 +23,9 @@ struct svbrdf_b200_ctx {
     float *d_in, *d_tg, *d_gr, *d_lin, *d_loss, *d_ws;
     float *h_in, *h_tg, *h_gr, *h_loss;      // pinned
     size_t ws_bytes;
-    cudaStream_t s_h2d, s_comp, s_d2h;
-    cudaEvent_t* ev_up;                      // per slice: upload done
+    cudaStream_t s_h2d, s_h2d2, s_comp, s_d2h;
+    cudaEvent_t* ev_up;                      // per slice: input upload done
+    cudaEvent_t* ev_up2;                     // per slice: target upload done
     cudaEvent_t* ev_k;                       // per slice: kernel done
     int max_slices;
 };
@@ -114,8 +115,10 @@ extern "C" void svbrdf_b200_ctx_destroy(svbrdf_b200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->ev_up) for (int i = 0; i < c->max_slices; ++i) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
     if (c->ev_k) for (int i = 0; i < c->max_slices; ++i) if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
-    free(c->ev_up); free(c->ev_k);
+    if (c->ev_up2) for (int i = 0; i < c->max_slices; ++i) if (c->ev_up2[i]) cudaEventDestroy(c->ev_up2[i]);
+    free(c->ev_up); free(c->ev_k); free(c->ev_up2);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_h2d2) cudaStreamDestroy(c->s_h2d2);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     cudaFree(c->d_in); cudaFree(c->d_tg); cudaFree(c->d_gr); cudaFree(c->d_lin); cudaFree(c->d_loss); cudaFree(c->d_ws);
@@ -150,14 +153,17 @@ extern "C" int svbrdf_b200_ctx_create(svbrdf_b200_ctx** out, int max_B, int max_
         CK(cudaMallocHost(&c->h_gr, bytes));
         CK(cudaMallocHost(&c->h_loss, 4 * sizeof(float)));
         CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_h2d2, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
         c->ev_up = (cudaEvent_t*)calloc(c->max_slices, sizeof(cudaEvent_t));
         c->ev_k = (cudaEvent_t*)calloc(c->max_slices, sizeof(cudaEvent_t));
-        if (!c->ev_up || !c->ev_k) { rc = svb_fail(SVBRDF_E_INVALID, "out of host memory"); goto done; }
+        c->ev_up2 = (cudaEvent_t*)calloc(c->max_slices, sizeof(cudaEvent_t));
+        if (!c->ev_up || !c->ev_k || !c->ev_up2) { rc = svb_fail(SVBRDF_E_INVALID, "out of host memory"); goto done; }
         for (int i = 0; i < c->max_slices; ++i) {
             CK(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_up2[i], cudaEventDisableTiming));
         }
         lin = (float*)malloc((size_t)W * sizeof(float));
         if (!lin) { rc = svb_fail(SVBRDF_E_INVALID, "out of host memory"); goto done; }
@@ -199,9 +205,11 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
             const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
             const size_t off = (size_t)b0 * c->map_floats, cnt = (size_t)(b1 - b0) * c->map_floats;
             CK(cudaMemcpyAsync(c->d_in + off, input_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
-            CK(cudaMemcpyAsync(c->d_tg + off, target_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaMemcpyAsync(c->d_tg + off, target_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d2));
             CK(cudaEventRecord(c->ev_up[i], c->s_h2d));
+            CK(cudaEventRecord(c->ev_up2[i], c->s_h2d2));
             CK(cudaStreamWaitEvent(c->s_comp, c->ev_up[i], 0));
+            CK(cudaStreamWaitEvent(c->s_comp, c->ev_up2[i], 0));
             rc = svb_launch_loss_range(c->d_in, c->d_tg, grad_host ? c->d_gr : nullptr, B, HW, c->W, scenes_host, N,
                                        c->d_lin, part_render, part_l1, false, 0.f, b0, b1 - b0, c->s_comp);
             if (rc) goto done;
@@ -219,7 +227,7 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
         *loss_host = c->h_loss[0];
     }
 done:
-    if (rc) { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); }
+    if (rc) { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_h2d2); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); }
     if (prev >= 0) cudaSetDevice(prev);
     return rc;
 }
