@@ -42,8 +42,11 @@ constexpr int kCapLarge = 796;   // records -> 28,656 B
 #define SVB_F2_MINB 3
 #endif
 template <typename T> struct Cfg;
-template <> struct Cfg<float> { static constexpr int kThreads = 256; static constexpr int kMinBlocks = 2; };
-template <> struct Cfg<F2> { static constexpr int kThreads = SVB_F2_THREADS; static constexpr int kMinBlocks = SVB_F2_MINB; };
+template <> struct Cfg<float> { static constexpr int kThreads = 256; static constexpr int kMinBlocks = 2; static constexpr int kRenderBwdMinBlocks = 2; };
+#ifndef SVB_RBWD_MINB
+#define SVB_RBWD_MINB 4
+#endif
+template <> struct Cfg<F2> { static constexpr int kThreads = SVB_F2_THREADS; static constexpr int kMinBlocks = SVB_F2_MINB; static constexpr int kRenderBwdMinBlocks = SVB_RBWD_MINB; };
 
 template <int CAP>
 struct SceneBlock {
@@ -245,7 +248,7 @@ render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
 }
 
 template <typename T, int CAP>
-__global__ void __launch_bounds__(Cfg<T>::kThreads)
+__global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kRenderBwdMinBlocks)
 render_bwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     const int b = blockIdx.y;
     const Where<T> w = locate<T>(a.HW, a.W, a.lin);

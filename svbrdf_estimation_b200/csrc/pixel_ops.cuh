@@ -157,16 +157,18 @@ SVB_DEV T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
         const bool logged = (c >= 3 && c < 6) || c >= 9;      // diffuse and specular use log(x + 0.01)
-        T d, w = LaneTraits<T>::splat(scale);
+        const T diff = vi[c] - vt[c];                         // sign(log a' - log b') = sign(a - b), exact at 0
         if (logged) {
-            const T a = vi[c] + kEpsL1, b = vt[c] + kEpsL1;
-            d = (vlg2(a) - vlg2(b)) * kLn2;
-            if (BWD) w = vrcp(a) * scale;
+            // |log a' - log b'| as one lg2 of the ratio; 1/a' is also d log(a')/da.  (This block runs once per
+            // pixel, but its MUFU burst is as long as a whole record iteration, so every MUFU saved here counts.)
+            const T ra = vrcp(vi[c] + kEpsL1);
+            const T l = vlg2((vt[c] + kEpsL1) * ra);
+            s = s + vnonzero(diff, vabs(l) * kLn2);
+            if (BWD) g[c] = g[c] + vsigned(diff, ra * scale);
         } else {
-            d = vi[c] - vt[c];
+            s = s + vabs(diff);
+            if (BWD) g[c] = g[c] + vsigned(diff, LaneTraits<T>::splat(scale));
         }
-        s = s + vabs(d);
-        if (BWD) g[c] = g[c] + vsigned(d, w);
     }
     return s;
 }
@@ -240,16 +242,23 @@ SVB_DEV void render_pixel(const T (&v)[12], T x, float y, const float* __restric
 template <typename T, int NC, int C0, typename IO>
 SVB_DEV void render_bwd_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec, int N,
                                 const float* __restrict__ gin, size_t HW, Acc<T, NC>& acc) {
+    T up[NC];                                   // upstream gradient of the NEXT record: loaded one iteration ahead
+#pragma unroll
+    for (int c = 0; c < NC; ++c) IO::ld(gin + (size_t)(C0 + c) * HW, up[c]);
     SVB_UNROLL1
-    for (int k = 0; k < N; ++k, rec += kRecFloats, gin += 3 * HW) {
+    for (int k = 0; k < N; ++k, rec += kRecFloats) {
+        T a[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[c] = up[c];
+        if (k + 1 < N) {
+            gin += 3 * HW;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) IO::ld(gin + (size_t)(C0 + c) * HW, up[c]);
+        }
         const Geo<T> g = make_geo<T>(x, y, rec);
         T AE[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            T a;
-            IO::ld(gin + (size_t)(C0 + c) * HW, a);
-            AE[c] = a * (g.fall * (rec[6 + C0 + c] * kInvPi));
-        }
+        for (int c = 0; c < NC; ++c) AE[c] = a[c] * (g.fall * (rec[6 + C0 + c] * kInvPi));
         Fwd<T, NC> f;
         shade_fwd<T, NC, true>(g, px, f);
         shade_bwd<T, NC>(g, px, f, AE, acc);

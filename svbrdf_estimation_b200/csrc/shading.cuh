@@ -123,6 +123,9 @@ SVB_DEV F2 vsigned(F2 d, F2 v) { return mk2(vsigned(lo(d), lo(v)), vsigned(hi(d)
 // is handled separately (see loss_kernel: bitwise-identical inputs are masked per pixel / per channel)
 SVB_DEV float vcopysign(float v, float d) { return copysignf(v, d); }
 SVB_DEV F2 vcopysign(F2 v, F2 d) { return mk2(copysignf(lo(v), lo(d)), copysignf(hi(v), hi(d))); }
+// (d != 0) ? v : 0 per lane
+SVB_DEV float vnonzero(float d, float v) { return d != 0.f ? v : 0.f; }
+SVB_DEV F2 vnonzero(F2 d, F2 v) { return mk2(lo(d) != 0.f ? lo(v) : 0.f, hi(d) != 0.f ? hi(v) : 0.f); }
 // (a >= b) ? v : 0 per lane, as a float factor
 SVB_DEV float vstep(float a, float b, float v) { return a >= b ? v : 0.f; }
 SVB_DEV F2 vstep(F2 a, float b, float v) { return mk2(lo(a) >= b ? v : 0.f, hi(a) >= b ? v : 0.f); }
