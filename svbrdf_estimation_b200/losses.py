@@ -33,103 +33,88 @@ def _check_pair(input, target):
         raise ValueError("input and target are on different devices")
 
 
+def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded=False):
+    """One C-ABI loss call on the current stream of ``b``'s device.  ``a`` is the differentiated argument
+    ([B,12,H,W] maps, or the [B,9,H,W] encoded network output when ``encoded``), ``grad`` its gradient buffer
+    (or None: forward only)."""
+    lib = _cabi.lib()
+    B, _, H, W = b.shape
+    N = records.shape[1]
+    gp = grad.data_ptr() if grad is not None else None
+    with torch.cuda.device(b.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if encoded:
+            status = lib.svbrdf_b200_mixed_loss_encoded_forward_backward(
+                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight), lin.data_ptr(),
+                out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream)
+        elif l1_weight is not None:
+            status = lib.svbrdf_b200_mixed_loss_forward_backward(
+                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight), lin.data_ptr(),
+                out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream)
+        elif grad is not None:
+            status = lib.svbrdf_b200_loss_forward_backward(
+                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(), gp,
+                ws.data_ptr(), ws_bytes, stream)
+        else:
+            status = lib.svbrdf_b200_loss_forward(
+                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
+                ws.data_ptr(), ws_bytes, stream)
+    _cabi.check(status)
+
+
 class _FusedLoss(torch.autograd.Function):
-    """loss (and d loss/d input computed in the same kernel pass) for given host scene records.
+    """Loss value and - computed in the same kernel pass - d loss / d input for given host scene records.
 
-    ``l1_weight is None`` -> RenderingLoss; otherwise MixedLoss with that weight, and the returned
-    tensor has 3 entries (mixed, rendering, map-L1)."""
+    ``l1_weight is None`` -> RenderingLoss, otherwise MixedLoss with that weight; ``encoded`` -> ``input`` is
+    the 9-channel network output.  Returns ``(loss, parts)``: ``loss`` is the differentiable 0-dim value,
+    ``parts = [rendering loss, map-L1 loss]`` is informational and marked non-differentiable."""
 
     @staticmethod
-    def forward(ctx, input, target, records, l1_weight):
-        B, _, H, W = input.shape
-        N = records.shape[1]
-        lib = _cabi.lib()
-        mixed = l1_weight is not None
-        out = torch.empty(3 if mixed else 1, device=input.device, dtype=torch.float32)
-        ws, ws_bytes = _workspace(B, N, H, W, input.device)
-        lin = coordinate_table(W, input.device)
+    def forward(ctx, input, target, records, l1_weight, encoded):
+        B, _, H, W = target.shape
+        dev = target.device
+        out = torch.empty(3, device=dev, dtype=torch.float32)
+        ws, ws_bytes = _workspace(B, records.shape[1], H, W, dev)
+        lin = coordinate_table(W, dev)
         want_in, want_tg = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        grad_in = torch.empty_like(input) if want_in else None
-        with torch.cuda.device(input.device):
-            stream = torch.cuda.current_stream().cuda_stream
-
-            def run(a, b, g):
-                gp = g.data_ptr() if g is not None else None
-                if mixed:
-                    _cabi.check(lib.svbrdf_b200_mixed_loss_forward_backward(
-                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight),
-                        lin.data_ptr(), out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream))
-                elif g is not None:
-                    _cabi.check(lib.svbrdf_b200_loss_forward_backward(
-                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(),
-                        out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream))
-                else:
-                    _cabi.check(lib.svbrdf_b200_loss_forward(
-                        a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(),
-                        out.data_ptr(), ws.data_ptr(), ws_bytes, stream))
-
-            run(input, target, grad_in)
-            grad_tg = None
-            if want_tg:
-                # the loss is symmetric in its arguments: d/d target = the same kernel with the roles swapped
-                grad_tg = torch.empty_like(target)
-                scratch = torch.empty_like(out)
-                keep, out = out, scratch
-                run(target, input, grad_tg)
-                out = keep
-        ctx.grads = (grad_in, grad_tg)
-        ctx.mixed = mixed
-        return out if mixed else out.reshape(())
+        grad_in = torch.empty_like(input) if (want_in or encoded) else None
+        _launch_loss(input, target, records, l1_weight, out, grad_in, ws, ws_bytes, lin, encoded)
+        grad_tg = None
+        if want_tg:
+            if encoded:
+                raise NotImplementedError("the gradient w.r.t. the target is not available for encoded input")
+            # the loss is symmetric in its arguments: d/d target = the same kernel with the roles swapped
+            grad_tg = torch.empty_like(target)
+            _launch_loss(target, input, records, l1_weight, torch.empty_like(out), grad_tg, ws, ws_bytes, lin)
+        ctx.grads = (grad_in if want_in else None, grad_tg)
+        loss, parts = out[0].reshape(()), out[1:3]
+        if l1_weight is None:
+            parts = torch.stack((loss.detach(), torch.zeros_like(loss)))
+        ctx.mark_non_differentiable(parts)
+        return loss, parts
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_loss, _grad_parts):
         if ctx.grads is None:
             raise RuntimeError("the fused rendering loss was already back-propagated; its gradient buffer "
                                "is handed to autograd on the first backward()")
-        grad_in, grad_tg = ctx.grads
-        ctx.grads = None
-        up = grad_out.reshape(-1)[0:1].to(torch.float32).contiguous()   # d/d(mixed or rendering loss)
-        if ctx.mixed and bool((grad_out.reshape(-1)[1:] != 0).any()):
-            raise NotImplementedError("only the first entry (the mixed loss) of the fused MixedLoss output "
-                                      "is differentiable")
+        grads, ctx.grads = ctx.grads, None
+        up = grad_loss.reshape(1).to(torch.float32).contiguous()
         lib = _cabi.lib()
-        for g in (grad_in, grad_tg):
+        for g in grads:
             if g is not None:
                 with torch.cuda.device(g.device):
+                    # in place; returns on the device when the upstream gradient is 1 (no host sync)
                     _cabi.check(lib.svbrdf_b200_scale_grad(g.data_ptr(), g.numel(), up.data_ptr(),
                                                            torch.cuda.current_stream().cuda_stream))
-        return grad_in, grad_tg, None, None
-
-
-class _FusedEncodedLoss(torch.autograd.Function):
-    """MixedLoss fed by the network's 9-channel encoded output; returns (mixed, rendering, map-L1)."""
-
-    @staticmethod
-    def forward(ctx, encoded, target, records, l1_weight):
-        B, _, H, W = target.shape
-        N = records.shape[1]
-        lib = _cabi.lib()
-        out = torch.empty(3, device=target.device, dtype=torch.float32)
-        ws, ws_bytes = _workspace(B, N, H, W, target.device)
-        lin = coordinate_table(W, target.device)
-        grad = torch.empty_like(encoded)
-        with torch.cuda.device(target.device):
-            _cabi.check(lib.svbrdf_b200_mixed_loss_encoded_forward_backward(
-                encoded.data_ptr(), target.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight),
-                lin.data_ptr(), out.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes,
-                torch.cuda.current_stream().cuda_stream))
-        ctx.grads = (grad, None)
-        ctx.mixed = True
-        return out
-
-    backward = staticmethod(lambda ctx, grad_out: _FusedLoss.backward(ctx, grad_out))
+        return grads[0], grads[1], None, None, None
 
 
 def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1):
     """``MixedLoss`` evaluated directly on the network's encoded output ``[B,9,H,W]`` (after tanh: normal xy,
     diffuse, roughness, specular in [-1,1]); the decode of models.py:334-346 / utils.py:73-98 and its chain
-    rule run inside the loss kernel.  Returns a 3-vector (mixed, rendering, map-L1); only
-    the first entry is differentiable."""
+    rule run inside the loss kernel (SURVEY.md 8f-3).  Returns ``(mixed, rendering, map_l1)`` 0-dim tensors;
+    only the first is differentiable."""
     if encoded.dim() != 4 or encoded.shape[1] != 9:
         raise ValueError("encoded must be [B,9,H,W], got %s" % (tuple(encoded.shape),))
     if encoded.dtype != torch.float32:
@@ -141,19 +126,21 @@ def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1):
     rec = as_host_records(records, b.shape[0])
     if rec.dim() != 3:
         raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
-    out = _FusedEncodedLoss.apply(e, b, rec, float(l1_weight))
-    return out if origin.type == "cuda" else out.to(origin)
+    loss, parts = _FusedLoss.apply(e, b, rec, float(l1_weight), True)
+    out = (loss, parts[0], parts[1])
+    return out if origin.type == "cuda" else tuple(t.to(origin) for t in out)
 
 
 def _fused_loss(input, target, records, l1_weight):
+    """-> differentiable 0-dim loss on the input's device (RenderingLoss, or MixedLoss when l1_weight is given)."""
     _check_pair(input, target)
     a, _, origin = as_device_maps(input, "input")
     b, _, _ = as_device_maps(target, "target")
     rec = as_host_records(records, a.shape[0])
     if rec.dim() != 3:
         raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
-    out = _FusedLoss.apply(a, b, rec, l1_weight)
-    return out if origin.type == "cuda" else out.to(origin)
+    loss, _ = _FusedLoss.apply(a, b, rec, l1_weight, False)
+    return loss if origin.type == "cuda" else loss.to(origin)
 
 
 def rendering_loss_with_records(input, target, records):
@@ -227,8 +214,7 @@ class MixedLoss(nn.Module):
         rl = self.rendering_loss
         if getattr(rl.renderer, "fused_rendering_loss", False):
             _check_pair(input, target)
-            out = _fused_loss(input, target, rl.sample_records(input.shape[0]), float(self.l1_weight))
-            return out[0]
+            return _fused_loss(input, target, rl.sample_records(input.shape[0]), float(self.l1_weight))
         return self.l1_weight * self.l1_loss(input, target) + rl(input, target)
 
     def forward_encoded(self, encoded, target):
