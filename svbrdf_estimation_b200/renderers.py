@@ -42,6 +42,8 @@ def as_device_maps(svbrdf, what="svbrdf"):
     if svbrdf.shape[-1] != svbrdf.shape[-2]:
         raise ValueError("only square maps are supported (renderers.py:73-76), got %dx%d"
                          % (svbrdf.shape[-2], svbrdf.shape[-1]))
+    if svbrdf.dtype in (torch.float16, torch.bfloat16):
+        svbrdf = svbrdf.float()          # e.g. a network output under autocast: the kernels compute in fp32
     if svbrdf.dtype != torch.float32:
         raise TypeError("%s must be float32 (the kernels compute in fp32), got %s" % (what, svbrdf.dtype))
     require_cuda()

@@ -343,3 +343,20 @@ def test_cuda_graph_capture_and_replay(S):
     graph.replay()
     torch.cuda.synchronize()
     assert float(out) == want and torch.equal(grad, want_g)
+
+
+def test_half_precision_inputs_are_upcast_and_second_device(S):
+    inp, tgt = synthetic_maps(2, 16, 3).cuda(), synthetic_maps(2, 16, 4).cuda()
+    cfg = O.sample_loss_configs(2)
+    x16 = inp.to(torch.bfloat16).requires_grad_(True)
+    loss = S.rendering_loss_with_records(x16, tgt, cfg)
+    loss.backward()
+    assert loss.dtype == torch.float32 and x16.grad.dtype == torch.bfloat16
+    ref = S.rendering_loss_with_records(x16.detach().float(), tgt, cfg)
+    assert float(loss.detach()) == float(ref)
+    if torch.cuda.device_count() > 1:                       # tensors on a device that is not the current one
+        a = inp.to("cuda:1").requires_grad_(True)
+        l1 = S.rendering_loss_with_records(a, tgt.to("cuda:1"), cfg)
+        l1.backward()
+        assert l1.device.index == 1 and a.grad.device.index == 1
+        assert abs(float(l1.detach()) - float(S.rendering_loss_with_records(inp, tgt, cfg))) <= 1e-7
