@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (per-GPU batch, size, N, n_random, n_specular, BASELINE.json config it is)
+    "c1": (8, 256, 9, 3, 6, "configs[0]: single-view RenderingLoss, batch 8 of 256x256 SVBRDF maps, 9 light/view configs (the reference's CPU-runnable case)"),
     "c2": (64, 256, 9, 3, 6, "configs[1]: single-view RenderingLoss fwd+bwd, batch 64 of 256x256 maps, 9 configs"),
     "c3": (32, 256, 27, 9, 18, "configs[2]: batch 32 of 256x256, 27 light/view configs"),
     "c4": (16, 1024, 9, 3, 6, "configs[3]: high-res 1024x1024 maps, batch 16, 9 configs"),

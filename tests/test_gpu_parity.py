@@ -353,7 +353,7 @@ def test_half_precision_inputs_are_upcast_and_second_device(S):
     loss.backward()
     assert loss.dtype == torch.float32 and x16.grad.dtype == torch.bfloat16
     ref = S.rendering_loss_with_records(x16.detach().float(), tgt, cfg)
-    assert float(loss.detach()) == float(ref)
+    assert abs(float(loss.detach()) - float(ref)) <= 1e-6 * float(ref)   # fwd+bwd vs forward-only kernel: rounding
     if torch.cuda.device_count() > 1:                       # tensors on a device that is not the current one
         a = inp.to("cuda:1").requires_grad_(True)
         l1 = S.rendering_loss_with_records(a, tgt.to("cuda:1"), cfg)
