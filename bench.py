@@ -161,6 +161,26 @@ def time_cpu_port(workload, steps, warmup, budget_s):
     return evals / sec / 1e9, sec, b, torch.get_num_threads()
 
 
+def time_gpu_eager_port(workload, dev, batch=2, steps=3):
+    """The same eager port on the GPU (what the reference does when main.py runs with --gpu-id): ~100 small
+    kernels per render call, 2*N render calls per sample -> launch-bound.  Bounded sample of `batch` maps."""
+    import torch
+    from svbrdf_estimation_b200 import environment as E
+    B, size, N, nr, ns, _ = WORKLOADS[workload]
+    b = min(batch, B)
+    inp, tgt = synthetic_maps(b, size, 1001).to(dev), synthetic_maps(b, size, 2001).to(dev)
+    torch.manual_seed(313)
+    cfg = E.sample_loss_configs(b, nr, ns)
+    cpu_port_step(inp, tgt, cfg)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(inp, tgt, cfg)
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    return b * size * size * N / sec / 1e9, sec, b
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -382,6 +402,15 @@ def run_ours(args):
                "sample": "first %d of %d maps of the workload, %dx%d, N=%d, 1 warm-up + 5 timed fwd+bwd passes (%.2f s each)"
                          % (b, B, size, size, N, sec)}
 
+    eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, sec, b = time_gpu_eager_port(args.workload, dev)
+            eager = {"value": v, "unit": UNIT, "kind": "port", "device": "same B200, eager PyTorch",
+                     "sample": "first %d of %d maps, fwd+bwd via autograd, %.2f s per pass" % (b, B, sec)}
+        except Exception as exc:          # informational leg only
+            eager = {"unavailable": repr(exc)[:200]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -391,7 +420,7 @@ def run_ours(args):
                        "scene_sampler_ms_per_step_host": sampler_ms},
             "value_per_gpu": value / world, "loss": loss_value,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "fp32_probes_tflops": probes,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * steps,
+            "cpu_baseline": cpu, "reference_port_eager_on_gpu": eager, "e2e": e2e, "gpu_launches": 2 * steps,
             "gpu_launches_note": "per step: 1 fused loss fwd+bwd kernel + 1 single-CTA finalize kernel",
             "clocks": sampler.summary(clock_note),
             "step_ms_with_event_per_step": {"min": per_step[0], "median": statistics.median(per_step), "max": per_step[-1], "n": len(per_step)}}
