@@ -156,7 +156,7 @@ SVBRDF_API int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* ctx, const float
 
 /* ---- measurement helpers (bench.py only) -------------------------------------------------------
  * Register-resident FP32 throughput probes used as measured roofline denominators.
- * kind: 0 = dependent-chain-free FFMA, 1 = packed fma.rn.f32x2, 2 = MUFU.RCP, 3 = FMUL+FADD mix.
+ * kind: 0 = independent scalar FFMA chains, 1 = packed fma.rn.f32x2 (FFMA2), 3 = FMUL+FADD mix (1 FLOP each).
  * Launches `blocks` CTAs of 256 threads running `iters` unrolled groups; *ops_per_thread_iter
  * receives the number of counted operations (FMA = 1 op) per thread per iteration.          */
 SVBRDF_API int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* sink_dev,

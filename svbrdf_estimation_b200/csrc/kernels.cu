@@ -291,13 +291,6 @@ probe_kernel(int iters, float* __restrict__ sink) {
                     const F2 t = vfma(mk2(r[i], r[i + 1]), mk2(m, m), mk2(c, c));
                     r[i] = lo(t); r[i + 1] = hi(t);
                 }
-            } else if (KIND == 2) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {       // volatile: each MUFU is issued (x -> 1/x -> x ...)
-                    float y;
-                    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r[i]));
-                    r[i] = y;
-                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) { r[i] = r[i] * m; r[i + 1] = r[i + 1] + c; }
@@ -578,7 +571,6 @@ extern "C" int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* 
     switch (kind) {
         case 0: probe_kernel<0><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
         case 1: probe_kernel<1><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
-        case 2: probe_kernel<2><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
         case 3: probe_kernel<3><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
         default: return fail(SVBRDF_E_INVALID, "unknown probe kind");
     }

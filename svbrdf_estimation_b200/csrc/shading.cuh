@@ -280,17 +280,18 @@ SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T, NC>& o
     const T hV = vfma(o.VN2, -0.5f, 0.5f), hL = vfma(o.LN2, -0.5f, 0.5f);
     const T rest = vfma(o.NH, w, vfma(hV, o.zV, hL * o.zL));
     const T Tk = o.iR - o.S * rest;
-    T gLN0, G;
+    T gLN0, gFsum;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const T gf = AE[c] * o.LN0;
         gLN0 = (c == 0) ? AE[c] * o.f[c] : vfma(AE[c], o.f[c], gLN0);
-        acc.gd[c] = vfma(gf, 1.f - o.F[c], acc.gd[c]);
-        acc.gs[c] = vfma(gf * o.Smd[c], g.omp5, acc.gs[c]);
         const T gfF = gf * o.F[c];
+        acc.gd[c] = (acc.gd[c] + gf) - gfF;                       // += gf (1 - F): two 2-operand adds beat sub + 3-operand fma
+        acc.gs[c] = vfma(gf * o.Smd[c], g.omp5, acc.gs[c]);
         acc.ga2[c] = vfma(gfF, Tk, acc.ga2[c]);
-        G = (c == 0) ? gfF * o.S : vfma(gfF, o.S, G);             // d loss / d ln S
+        gFsum = (c == 0) ? gfF : gFsum + gfF;
     }
+    const T G = gFsum * o.S;                                      // d loss / d ln S
     // d ln S / d NH = 4 NH (1-a2) / q [q unclamped];  d ln S / d VN = -(wV + VN (1-a2)) zV;  same for LN.
     // clamp(min=...) passes the gradient where the raw value is >= the bound (renderers.py:48-52,96).
     const T gNHr = (G * (p.oma2 * w)) * vstep(o.NHr, kClamp, 2.f);
