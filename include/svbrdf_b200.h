@@ -136,7 +136,8 @@ SVBRDF_API int svbrdf_b200_mixed_loss_encoded_forward_backward(const float* enco
 
 /* ---- host-buffer entry point (the call a non-PyTorch caller makes) --------------------------
  * A context owns pinned staging buffers, device buffers and copy/compute streams for problems
- * up to the given size on the current device.                                                */
+ * up to the given size on the current device.  One call at a time per context (use one context per
+ * host thread); different contexts are independent.                                          */
 typedef struct svbrdf_b200_ctx svbrdf_b200_ctx;
 
 SVBRDF_API int svbrdf_b200_ctx_create(svbrdf_b200_ctx** out, int max_B, int max_N, int H, int W);
