@@ -360,3 +360,21 @@ def test_half_precision_inputs_are_upcast_and_second_device(S):
         l1.backward()
         assert l1.device.index == 1 and a.grad.device.index == 1
         assert abs(float(l1.detach()) - float(S.rendering_loss_with_records(inp, tgt, cfg))) <= 1e-7
+
+
+def test_degenerate_maps_stay_finite_and_match(S, golden):
+    """Zero normals, zero / one albedos, zero and >1 roughness, light and camera straight above a pixel."""
+    g = golden("loss_bench")
+    tgt = g["target"][:, :, :8, :8].copy()
+    inp = np.zeros_like(tgt)
+    inp[0, 3:6], inp[0, 6:9], inp[0, 9:12] = 0.0, 0.0, 1.0
+    inp[1, 0:3] = np.array([0.0, 0.0, 1.0], dtype=np.float32).reshape(3, 1, 1)
+    inp[1, 3:6], inp[1, 6:9], inp[1, 9:12] = 1.0, 1.5, 0.0
+    cfg = g["configs"][:, :4].copy()
+    cfg[0, 0] = [0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 20.0, 20.0, 20.0]
+    cfg[1, 1] = [-1.0, 1.0, 0.5, -1.0, 1.0, 0.5, 50.0, 50.0, 50.0]
+    l64, g64 = O.rendering_loss_and_grad(torch.from_numpy(inp).double(), torch.from_numpy(tgt).double(), torch.from_numpy(cfg))
+    loss, grad = ours_loss_and_grad(S, inp, tgt, cfg)
+    assert np.isfinite(loss) and np.isfinite(grad).all()
+    assert abs(loss - float(l64)) <= 5e-6 * float(l64)
+    assert parity.rel_l2(grad, g64.numpy()) <= 3e-4

@@ -117,3 +117,25 @@ def test_encoded_input_loss_and_gradient(golden, lanes):
     g64 = e64.grad.numpy()
     for name, s in (("normal_xy", slice(0, 2)), ("diffuse", slice(2, 5)), ("roughness", slice(5, 6)), ("specular", slice(6, 9))):
         assert parity.rel_l2(grad[:, s], g64[:, s]) <= 1.5e-4, (name, parity.rel_l2(grad[:, s], g64[:, s]))
+
+
+def test_degenerate_maps_stay_finite_and_match(golden):
+    """Zero normals, zero / one albedos, zero and >1 roughness, light and camera straight above a pixel."""
+    g = golden("loss_bench")
+    tgt = g["target"][:, :, :8, :8].copy()
+    inp = np.zeros_like(tgt)
+    inp[0, 0:3] = 0.0                                   # null normal: every dot product clamps
+    inp[0, 3:6], inp[0, 6:9], inp[0, 9:12] = 0.0, 0.0, 1.0
+    inp[1, 0:3] = np.array([0.0, 0.0, 1.0], dtype=np.float32).reshape(3, 1, 1)
+    inp[1, 3:6], inp[1, 6:9], inp[1, 9:12] = 1.0, 1.5, 0.0   # roughness above 1
+    cfg = g["configs"][:, :4].copy()
+    cfg[0, 0] = [0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 20.0, 20.0, 20.0]          # camera == light, above the centre
+    cfg[1, 1] = [-1.0, 1.0, 0.5, -1.0, 1.0, 0.5, 50.0, 50.0, 50.0]        # both above the top-left corner pixel
+    tc = torch.from_numpy(cfg)
+    l64, g64 = O.rendering_loss_and_grad(torch.from_numpy(inp).double(), torch.from_numpy(tgt).double(), tc)
+    assert torch.isfinite(l64) and torch.isfinite(g64).all()
+    for lanes in (1, 2):
+        loss, grad = emu.loss_forward_backward(inp, tgt, cfg, lanes)
+        assert np.isfinite(loss) and np.isfinite(grad).all()
+        assert abs(loss - float(l64)) <= 5e-6 * float(l64)
+        assert parity.rel_l2(grad, g64.numpy()) <= 3e-4, parity.rel_l2(grad, g64.numpy())
