@@ -188,6 +188,35 @@ def main():
                                 ref_utils.encode_as_unit_interval(s))
     np.savez(os.path.join(HERE, "decode.npz"), encoded=enc.numpy(), decoded_f32=dec.numpy())
 
+    # 7. dataset input synthesis (dataset.py:162-221): scenes, renders, noise, clamp -----------------------
+    for stub in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(stub, types.ModuleType(stub))
+    import dataset as ref_dataset  # noqa: E402
+    captured = []
+
+    class Recorder(ref_renderers.LocalRenderer):
+        def render(self, scene, svbrdf):
+            captured.append(np.concatenate([np.asarray(scene.camera.pos, dtype=np.float32),
+                                            np.asarray(scene.light.pos, dtype=np.float32),
+                                            np.asarray(scene.light.color, dtype=np.float32)]))
+            return super().render(scene, svbrdf)
+
+    keep_cls = ref_renderers.LocalRenderer
+    ref_renderers.LocalRenderer = Recorder
+    try:
+        maps = synthetic_maps(1, 16, 1005)[0]
+        out = {"svbrdf": maps.numpy()}
+        for tag, aug in (("plain", False), ("aug", True)):
+            captured.clear()
+            torch.manual_seed(4242)
+            fake = types.SimpleNamespace(use_augmentation=aug)
+            imgs = ref_dataset.SvbrdfDataset.render_inputs(fake, maps, 3)
+            out["inputs_" + tag] = imgs.numpy()
+            out["records_" + tag] = np.stack(captured)
+        np.savez(os.path.join(HERE, "dataset_inputs.npz"), seed=np.int64(4242), **out)
+    finally:
+        ref_renderers.LocalRenderer = keep_cls
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-20s %8.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

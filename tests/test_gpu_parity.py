@@ -378,3 +378,17 @@ def test_degenerate_maps_stay_finite_and_match(S, golden):
     assert np.isfinite(loss) and np.isfinite(grad).all()
     assert abs(loss - float(l64)) <= 5e-6 * float(l64)
     assert parity.rel_l2(grad, g64.numpy()) <= 3e-4
+
+
+def test_dataset_input_synthesis_matches_reference(S, golden):
+    """inputs.render_inputs == SvbrdfDataset.render_inputs (dataset.py:162-221) for the same seed."""
+    from svbrdf_estimation_b200 import inputs as I
+    g = golden("dataset_inputs")
+    for tag, aug in (("plain", False), ("aug", True)):
+        for dev in ("cuda", "cpu"):
+            torch.manual_seed(int(g["seed"]))
+            got = I.render_inputs(torch.from_numpy(g["svbrdf"]).to(dev), 3, use_augmentation=aug)
+            assert got.device.type == dev and got.shape == (3, 3, 16, 16)
+            np.testing.assert_allclose(got.cpu().numpy(), g["inputs_" + tag], rtol=2e-4, atol=2e-5)
+    fast = I.render_inputs(torch.from_numpy(g["svbrdf"]).cuda(), 4, use_augmentation=True, noise="device")
+    assert fast.shape == (4, 3, 16, 16) and float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0

@@ -211,3 +211,23 @@ def test_native_scene_sampler():
     assert (spec[..., 2] > 0).all() and (spec[..., 5] > 0).all()
     s = E.NativeSceneSampler(seed=1)
     assert not torch.equal(s(8), s(8))            # fresh scenes per call
+
+
+def test_input_scene_sampler_and_noise_stream_match_reference(golden):
+    """dataset.py:162-221: scene records bit-exact; with the render kernels' algebra (host emulation) and the
+    same generator stream for the sensor noise the final clamped images agree with the reference's."""
+    from svbrdf_estimation_b200 import inputs as I
+    from tests.emulation import host as emu
+    g = golden("dataset_inputs")
+    for tag, aug in (("plain", False), ("aug", True)):
+        torch.manual_seed(int(g["seed"]))
+        rec = I.sample_input_scenes(3, aug)
+        np.testing.assert_array_equal(rec.numpy(), g["records_" + tag])
+        images = torch.from_numpy(emu.render_forward(g["svbrdf"][None], rec.numpy()))[0]       # [3,3,H,W]
+        outs = []
+        for k in range(3):
+            std = torch.exp(torch.empty(1).normal_(mean=I.NOISE_LOG_STD[0], std=I.NOISE_LOG_STD[1])).numpy()[0]
+            noise = torch.zeros(1, 3, 16, 16).normal_(mean=0.0, std=float(std))
+            outs.append(torch.clamp(images[k:k + 1] + noise, min=0.0, max=1.0))
+        got = torch.cat(outs).numpy()
+        np.testing.assert_allclose(got, g["inputs_" + tag], rtol=2e-4, atol=2e-5)
