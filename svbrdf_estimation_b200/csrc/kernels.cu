@@ -355,6 +355,14 @@ static inline int batch_per_launch(int N, int per_batch, int cap) {
     return bc > 65535 ? 65535 : bc;
 }
 
+// When the records of `total` batch elements do not fit one parameter block, split into equal launches
+// (e.g. 32 elements with a cap of 29 -> 16 + 16, not 29 + 3: a 3-element launch fills under two waves).
+static inline int balanced_chunk(int total, int cap) {
+    if (total <= cap) return total > 0 ? total : 1;
+    const int launches = (total + cap - 1) / cap;
+    return (total + launches - 1) / launches;
+}
+
 template <int CAP, int THREADS, typename Args, typename Kernel>
 static cudaError_t launch_with_scenes(Kernel kernel, dim3 grid, const Args& args, const float* recs, int nrec,
                                       cudaStream_t st) {
@@ -415,7 +423,7 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
     a.scale_render = (float)(1.0 / ((double)B * N * 3.0 * HW));
     a.scale_l1 = (float)((double)l1_weight / ((double)B * 3.0 * HW));
     const bool small = !encoded && (size_t)bn * N <= (size_t)kCapSmall;
-    const int bc_max = batch_per_launch(N, 1, small ? kCapSmall : kCapLarge);
+    const int bc_max = balanced_chunk(bn, batch_per_launch(N, 1, small ? kCapSmall : kCapLarge));
     for (int s0 = b0; s0 < b0 + bn; s0 += bc_max) {
         const int bc = (b0 + bn - s0 < bc_max) ? (b0 + bn - s0) : bc_max;
         a.input = input + (size_t)s0 * cin * HW;
@@ -524,7 +532,7 @@ static int render_impl(const float* maps, int B, int H, int W, const float* scen
     a.lin = lin; a.HW = HW; a.W = W; a.N = N; a.per_batch = per_batch ? 1 : 0;
     const size_t nrec_total = per_batch ? (size_t)B * N : (size_t)N;
     const bool small = nrec_total <= (size_t)kCapSmall;
-    const int bc_max = batch_per_launch(N, per_batch, small ? kCapSmall : kCapLarge);
+    const int bc_max = balanced_chunk(B, batch_per_launch(N, per_batch, small ? kCapSmall : kCapLarge));
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = (B - b0 < bc_max) ? (B - b0) : bc_max;
         a.maps = maps + (size_t)b0 * 12 * HW;
