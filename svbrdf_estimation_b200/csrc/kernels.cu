@@ -29,7 +29,7 @@ namespace svb {
 // Kernel parameters may total 32,764 bytes on sm_70+ with CUDA >= 12.1.  Two capacities keep the
 // parameter copy small for the common render(scene, maps) call.
 constexpr int kCapSmall = 64;    // records ->  2,304 B
-constexpr int kCapLarge = 796;   // records -> 28,656 B
+constexpr int kCapLarge = 900;   // records -> 32,400 B (+ <= 96 B of other arguments < 32,764)
 
 // Threads per CTA and the occupancy promised to ptxas (register cap) by lane type.  The packed
 // kernels hold two pixels of state per thread; 128 threads x 3 CTAs/SM (<= 170 registers) measured
@@ -52,6 +52,7 @@ template <int CAP>
 struct SceneBlock {
     float v[CAP * kRecFloats];
 };
+static_assert(sizeof(SceneBlock<kCapLarge>) + 128 <= 32764, "scene records + arguments must fit the kernel parameter space");
 
 struct LossArgs {
     const float* input;    // [Bc,12,H,W] (already offset to this launch's first batch element)
@@ -328,7 +329,7 @@ int svb_check_shape(int B, int H, int W, int N) {
     if (B <= 0 || H <= 0 || W <= 0 || N <= 0) return fail(SVBRDF_E_INVALID, "B, H, W and N must be positive");
     if (H != W) return fail(SVBRDF_E_INVALID, "maps must be square (H == W), as in renderers.py:73-76");
     if ((long long)H * W > (1LL << 28)) return fail(SVBRDF_E_TOO_LARGE, "H*W exceeds 2^28 pixels");
-    if (N > kCapLarge) return fail(SVBRDF_E_TOO_LARGE, "more than 796 scene records per batch element");
+    if (N > kCapLarge) return fail(SVBRDF_E_TOO_LARGE, "more than 900 scene records per batch element");
     return 0;
 }
 
