@@ -42,8 +42,9 @@ def rf_cycles(body):
 def main():
     pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else r"loss_kernelINS_2F2ELb1ELb0ELb1ELb0ELi900")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    p = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-                        "-Xptxas", "-v", "-cubin", "-o", OUT, SRC], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    extra = os.environ.get("SVB_EXTRA_FLAGS", "").split()        # e.g. SVB_EXTRA_FLAGS="-DSVB_F2_MINB=2" for experiments
+    p = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"] + extra +
+                       ["-Xptxas", "-v", "-cubin", "-o", OUT, SRC], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode:
         print(p.stdout)
         return 1
