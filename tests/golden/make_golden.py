@@ -217,6 +217,30 @@ def main():
     finally:
         ref_renderers.LocalRenderer = keep_cls
 
+    # 8. real materials: 48x48 crops of the reference's toy data (mip/data/{train,test}/*.png), maps read like
+    #    dataset.py:105-136 (PNG/255; normals = 2*v - 1, NOT re-normalised; roughness as stored) ---------------
+    from PIL import Image
+
+    def read_maps(path, top, left, size=48):
+        full = torch.from_numpy(np.asarray(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0).permute(2, 0, 1)
+        parts = torch.cat(full.unsqueeze(0).chunk(14, dim=-1), 0)               # 10 inputs + 4 maps, 256 px each
+        n, d, r, sp = parts[10] * 2 - 1, parts[11], parts[12], parts[13]
+        return torch.cat((n, d, r, sp), dim=0)[:, top:top + size, left:left + size].contiguous()
+
+    data = os.path.join(REF, "data")
+    brick = os.path.join(data, "train", "0_10_brick_uneven_stones_0.png")
+    parquet = os.path.join(data, "train", "10_1_parquet_floor_0.png")
+    foam = os.path.join(data, "test", "11_20_SynteticFoam_0.png")
+    inp = torch.stack((read_maps(brick, 100, 60), read_maps(foam, 30, 150)))
+    tgt = torch.stack((read_maps(parquet, 64, 64), read_maps(brick, 10, 10)))
+    cfg = sample_configs(ref_env, 2024, 2, 3, 6)
+    out = {"input": inp.numpy(), "target": tgt.numpy(), "configs": cfg.numpy()}
+    for name, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        loss, grad, renders = reference_loss(ref, dtype, inp, tgt, cfg, 3)
+        out["loss_" + name] = loss
+        out["grad_" + name] = grad.astype(np.float32)             # stored in fp32: 6e-8 relative, far below the tolerances
+    np.savez_compressed(os.path.join(HERE, "loss_real.npz"), **out)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-20s %8.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

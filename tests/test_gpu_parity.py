@@ -31,7 +31,7 @@ def ours_loss_and_grad(S, inp, tgt, cfg):
 
 # ---- golden fixtures (outputs of the unmodified reference, fp32 and fp64) ------------------------
 
-@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27"])
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27", "loss_real"])
 def test_loss_and_gradient_vs_reference(S, golden, fixture):
     g = golden(fixture)
     loss, grad = ours_loss_and_grad(S, g["input"], g["target"], g["configs"])

@@ -12,7 +12,7 @@ from tests.emulation import host as emu
 
 
 @pytest.mark.parametrize("lanes", [1, 2])
-@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27"])
+@pytest.mark.parametrize("fixture", ["loss_bench", "loss_stress", "loss_n27", "loss_real"])
 def test_loss_and_gradient_three_way(golden, fixture, lanes):
     g = golden(fixture)
     loss, grad = emu.loss_forward_backward(g["input"], g["target"], g["configs"], lanes)
