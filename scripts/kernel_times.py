@@ -17,6 +17,8 @@ from svbrdf_estimation_b200 import environment as E     # noqa: E402
 def main():
     w = sys.argv[1] if len(sys.argv) > 1 else "c2"
     B, size, N, nr, ns, _ = bench.WORKLOADS[w]
+    if os.environ.get("SVB_VARIANT_LIB"):                 # time a variant build (scripts/variant_bench.py build ...)
+        _cabi.LIB_PATH = os.environ["SVB_VARIANT_LIB"]
     lib = _cabi.lib()
     dev = torch.device("cuda", 0)
     inp, tgt = bench.synthetic_maps(B, size, 1).to(dev), bench.synthetic_maps(B, size, 2).to(dev)

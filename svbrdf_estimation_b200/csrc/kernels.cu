@@ -154,6 +154,10 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
     constexpr int CIN = ENC ? 9 : 12;
     __shared__ float red[THREADS / 32];
+    // Programmatic dependent launch: the finalize kernel queued behind this grid may be scheduled as soon as
+    // every CTA of this grid is resident (it then waits in griddepcontrol.wait for this grid to complete and
+    // flush), so its launch latency overlaps the last wave instead of following it.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int b = blockIdx.y;
     const Where<T> w = locate<T>(a.HW, a.W, a.lin);
     const size_t off = (size_t)b * 12 * a.HW + w.p;
@@ -199,6 +203,7 @@ finalize_kernel(const float* __restrict__ part_render, const float* __restrict__
                 double mul_render, double mul_l1, float l1_weight, float* __restrict__ out, int n_out) {
     __shared__ double sm[2][32];
     double s0 = 0.0, s1 = 0.0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // all loss-kernel grids before us are complete and visible
     // 8 independent loads in flight per thread; the summation order is fixed by (thread, i)
     for (int base = threadIdx.x; base < count; base += 8 * 1024) {
         float v[8], u[8];
@@ -248,9 +253,55 @@ render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
     render_pixel<T, DeviceIO>(v, w.x, w.y, rec, a.N, out, (size_t)a.HW, w.live);
 }
 
+// Per-thread ring of upstream-gradient records in shared memory, filled with cp.async (LDGSTS): kDepth records
+// (3 planes x the thread's pixels each) are in flight per thread without holding registers, which is what this
+// HBM-latency-bound kernel needs (12 N bytes per pixel stream through it).  A thread only ever reads back what it
+// copied itself, so cp.async.wait_group is the only synchronisation.  Layout [slot][channel][thread]: conflict-free.
+#ifndef SVB_RING_DEPTH
+#define SVB_RING_DEPTH 3
+#endif
+template <typename T>
+struct RingIO {
+    static constexpr int kDepth = SVB_RING_DEPTH, kSlots = SVB_RING_DEPTH + 1;
+    static constexpr int kBytes = 4 * LaneTraits<T>::kLanes;
+    static constexpr int kStride = Cfg<T>::kThreads * kBytes;          // bytes per (slot, channel)
+    uint32_t base;                                                      // shared-space address of this thread's cell 0
+    int head, tail;
+    __device__ __forceinline__ explicit RingIO(float* smem) {
+        base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * kBytes;
+    }
+    __device__ __forceinline__ void reset() { head = tail = 0; }
+    template <int NC>
+    __device__ __forceinline__ void fetch(const float* p, size_t HW) {
+        const uint32_t dst = base + head * (3 * kStride);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + c * kStride), "l"(p + (size_t)c * HW), "n"(kBytes) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        head = (head + 1 == kSlots) ? 0 : head + 1;
+    }
+    __device__ __forceinline__ void skip() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    template <int NC>
+    __device__ __forceinline__ void take(T (&a)[NC]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDepth) : "memory");   // all but the kDepth newest groups have landed
+        const uint32_t src = base + tail * (3 * kStride);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) ld_cell(src + c * kStride, a[c]);
+        tail = (tail + 1 == kSlots) ? 0 : tail + 1;
+    }
+    static __device__ __forceinline__ void ld_cell(uint32_t addr, float& v) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); }
+    static __device__ __forceinline__ void ld_cell(uint32_t addr, F2& v) {
+        float x, y;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(addr));
+        v = mk2(x, y);
+    }
+};
+
 template <typename T, int CAP>
 __global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kRenderBwdMinBlocks)
 render_bwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
+    __shared__ __align__(16) float ring_mem[RingIO<T>::kSlots * 3 * Cfg<T>::kThreads * LaneTraits<T>::kLanes];
+    RingIO<T> ring(ring_mem);
     const int b = blockIdx.y;
     const Where<T> w = locate<T>(a.HW, a.W, a.lin);
     T v[12], g[12];
@@ -258,7 +309,7 @@ render_bwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
     load12<T>(a.maps + off, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
     const float* gin = a.gimages + (size_t)b * a.N * 3 * a.HW + w.p;
-    render_bwd_pixel<T, DeviceIO>(v, w.x, w.y, rec, a.N, gin, (size_t)a.HW, g);
+    render_bwd_pixel<T, RingIO<T>>(v, w.x, w.y, rec, a.N, gin, (size_t)a.HW, g, ring);
     if (w.live) store12<T>(a.gmaps + off, a.HW, g);
 }
 
@@ -452,9 +503,15 @@ int svb_launch_finalize(const float* part_render, const float* part_l1, int B, i
     // ln2 converts the log2 differences to natural log; 1/M is the mean of losses.py:50.
     const double mul_render = (double)kLn2 / ((double)B * N * 3.0 * HW);
     const double mul_l1 = 1.0 / ((double)B * 3.0 * HW);
-    finalize_kernel<<<1, 1024, 0, st>>>(part_render, mixed ? part_l1 : nullptr, (int)total_ctas, mul_render, mul_l1,
-                                        mixed ? l1_weight : 0.f, out, n_out);
-    return cuda_status(cudaGetLastError(), "finalize_kernel launch");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, finalize_kernel, part_render, mixed ? part_l1 : (const float*)nullptr,
+                                             (int)total_ctas, mul_render, mul_l1, mixed ? l1_weight : 0.f, out, n_out);
+    return cuda_status(e, "finalize_kernel launch");
 }
 
 static int loss_impl(const float* input, const float* target, int B, int H, int W, const float* scenes, int N,

@@ -58,30 +58,65 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
     for (int k = 0; k < N; ++k) {
         const float* __restrict__ rk = rec + k * kRecFloats;
         const Geo<T> g = make_geo<T>(x, y, rk);
-        Fwd<T, NC> fi, ft;
+        Fwd<T> fi, ft;
         shade_fwd<T, NC, BWD>(g, pi, fi);
         shade_fwd<T, NC, false>(g, pt, ft);
-        T E[NC], ELi[NC], ELt[NC], AE[NC];
+        // radiance + 0.1 of both maps (losses.py:46-47); E = light colour * falloff / pi
+        T E[NC], fin[NC], xi[NC], xt[NC];
+        if (GREY) {
+            E[0] = g.fall * (rk[6 + C0] * kInvPi);
+            radiance_plus_eps_grey<T, NC>(g, pt, ft, E[0] * ft.LN0, kEpsRender, xt);
+            if (BWD) {                                                     // the gradient of LN0 needs f' itself
+                brdf_values<T, NC>(g, pi, fi, fin);
+                const T ELi = E[0] * fi.LN0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) xi[c] = vfma(fin[c], ELi, kEpsRender);
+            } else {
+                radiance_plus_eps_grey<T, NC>(g, pi, fi, E[0] * fi.LN0, kEpsRender, xi);
+            }
+        } else {
+            T ftg[NC];
+            brdf_values<T, NC>(g, pi, fi, fin);
+            brdf_values<T, NC>(g, pt, ft, ftg);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                E[c] = g.fall * (rk[6 + C0 + c] * kInvPi);
+                xi[c] = vfma(fin[c], E[c] * fi.LN0, kEpsRender);
+                xt[c] = vfma(ftg[c], E[c] * ft.LN0, kEpsRender);
+            }
+        }
+        T A[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            if (!GREY || c == 0) {
-                E[c] = g.fall * (rk[6 + C0 + c] * kInvPi);                // light colour * falloff / pi
-                ELi[c] = E[c] * fi.LN0; ELt[c] = E[c] * ft.LN0;
-            } else {
-                E[c] = E[0]; ELi[c] = ELi[0]; ELt[c] = ELt[0];
-            }
-            const T xi = vfma(fi.f[c], ELi[c], kEpsRender);                // radiance + 0.1 (losses.py:46-47)
-            const T xt = vfma(ft.f[c], ELt[c], kEpsRender);
             // log(xt) - log(xi) as ONE lg2 of the ratio: 1/xi is needed for the gradient anyway.
-            const T ix = vrcp(xi);
-            const T l = vlg2(xt * ix);
+            const T ix = vrcp(xi[c]);
+            const T l = vlg2(xt[c] * ix);
             lsum = lsum + vabs(l);
             // d|l|/d xi = -sign(l)/xi: the accumulators carry +sign(l)/xi and the caller applies the minus
             // with the final scale.  sign(0) is taken as +1 here: an exact 0 only arises from inputs that
             // are bitwise identical for this channel, and those are masked in loss_pixel (losses.py:50).
-            if (BWD) AE[c] = vcopysign(ix, l) * E[c];
+            if (BWD) A[c] = vcopysign(ix, l);
         }
-        if (BWD) shade_bwd<T, NC>(g, pi, fi, AE, acc);
+        if (BWD) {
+            T gf[NC], gLN0;
+            if (GREY) {
+                const T ELi = E[0] * fi.LN0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    gf[c] = A[c] * ELi;
+                    gLN0 = (c == 0) ? A[c] * fin[c] : vfma(A[c], fin[c], gLN0);
+                }
+                gLN0 = gLN0 * E[0];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const T AE = A[c] * E[c];
+                    gf[c] = AE * fi.LN0;
+                    gLN0 = (c == 0) ? AE * fin[c] : vfma(AE, fin[c], gLN0);
+                }
+            }
+            shade_bwd<T, NC>(g, pi, fi, gf, gLN0, acc);
+        }
     }
     return lsum;
 }
@@ -98,11 +133,13 @@ SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, 
     const T l = loss_records<T, 1, C, BWD, GREY>(pi, pt, x, y, rec, N, acc);
     if (BWD) {
         const T ns = vsel(live, LaneTraits<T>::splat(nscale), 0.f);    // masked lanes: scale 0
+        T gd[1], gs[1];
+        acc_albedo_grads<T, 1>(acc, &vi[3 + C], &vi[9 + C], gd, gs);
 #pragma unroll
         for (int j = 0; j < 3; ++j) g[j] = vfma(acc.gn[j], ns, g[j]);
-        g[3 + C] = acc.gd[0] * ns;
+        g[3 + C] = gd[0] * ns;
         g[6 + C] = (acc.ga2[0] * ns) * rough_chain(vi[6 + C]);
-        g[9 + C] = acc.gs[0] * ns;
+        g[9 + C] = gs[0] * ns;
     }
     return vsel(live, l, 0.f);
 }
@@ -131,12 +168,14 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
         if (BWD) {
             const T ns = vsel(d0, LaneTraits<T>::splat(nscale), 0.f);  // fully identical pixels: scale 0
             const T chain = rough_chain(vi[6]) * ns;
+            T gd[3], gs[3];
+            acc_albedo_grads<T, 3>(acc, &vi[3], &vi[9], gd, gs);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 g[c] = acc.gn[c] * ns;
-                g[3 + c] = acc.gd[c] * ns;
+                g[3 + c] = gd[c] * ns;
                 g[6 + c] = acc.ga2[c] * chain;
-                g[9 + c] = acc.gs[c] * ns;
+                g[9 + c] = gs[c] * ns;
             }
         }
         return vsel(d0, l, 0.f);
@@ -217,12 +256,14 @@ SVB_DEV void render_records(const Pix<T, NC>& px, T x, float y, const float* __r
     SVB_UNROLL1
     for (int k = 0; k < N; ++k, rec += kRecFloats, out += 3 * HW) {
         const Geo<T> g = make_geo<T>(x, y, rec);
-        Fwd<T, NC> f;
+        Fwd<T> f;
         shade_fwd<T, NC, false>(g, px, f);
+        T fv[NC];
+        brdf_values<T, NC>(g, px, f, fv);
         if (live) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c)   // renderers.py:100 (f carries the factor pi)
-                IO::st(out + (size_t)(C0 + c) * HW, f.f[c] * ((g.fall * (rec[6 + C0 + c] * kInvPi)) * f.LN0));
+            for (int c = 0; c < NC; ++c)   // renderers.py:100 (f' carries the factor pi)
+                IO::st(out + (size_t)(C0 + c) * HW, fv[c] * ((g.fall * (rec[6 + C0 + c] * kInvPi)) * f.LN0));
         }
     }
 }
@@ -239,68 +280,79 @@ SVB_DEV void render_pixel(const T (&v)[12], T x, float y, const float* __restric
     }
 }
 
+// The upstream gradient (N x 3 planes per batch element) is the only per-record memory traffic of the path.  It is
+// streamed through a per-thread ring (IO = the kernel's RingIO: cp.async into shared memory, kDepth records in
+// flight, no registers held by the loads in flight; host emulation: a plain array): `ring.fetch` enqueues the NC
+// values of one record, `ring.take` waits for the oldest outstanding record and returns it.
 template <typename T, int NC, int C0, typename IO>
 SVB_DEV void render_bwd_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec, int N,
-                                const float* __restrict__ gin, size_t HW, Acc<T, NC>& acc) {
-    T up[NC];                                   // upstream gradient of the NEXT record: loaded one iteration ahead
+                                const float* __restrict__ gin, size_t HW, Acc<T, NC>& acc, IO& ring) {
+    gin += (size_t)C0 * HW;
+    ring.reset();
 #pragma unroll
-    for (int c = 0; c < NC; ++c) IO::ld(gin + (size_t)(C0 + c) * HW, up[c]);
+    for (int j = 0; j < IO::kDepth; ++j) {
+        if (j < N) ring.template fetch<NC>(gin + (size_t)j * 3 * HW, HW); else ring.skip();
+    }
     SVB_UNROLL1
     for (int k = 0; k < N; ++k, rec += kRecFloats) {
+        if (k + IO::kDepth < N) ring.template fetch<NC>(gin + (size_t)(k + IO::kDepth) * 3 * HW, HW); else ring.skip();
         T a[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) a[c] = up[c];
-        if (k + 1 < N) {
-            gin += 3 * HW;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) IO::ld(gin + (size_t)(C0 + c) * HW, up[c]);
-        }
+        ring.template take<NC>(a);
         const Geo<T> g = make_geo<T>(x, y, rec);
-        T AE[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) AE[c] = a[c] * (g.fall * (rec[6 + C0 + c] * kInvPi));
-        Fwd<T, NC> f;
+        Fwd<T> f;
         shade_fwd<T, NC, true>(g, px, f);
-        shade_bwd<T, NC>(g, px, f, AE, acc);
+        T fv[NC], gf[NC], gLN0;
+        brdf_values<T, NC>(g, px, f, fv);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const T AE = a[c] * (g.fall * (rec[6 + C0 + c] * kInvPi));    // d loss / d radiance_c * E'_c
+            gf[c] = AE * f.LN0;
+            gLN0 = (c == 0) ? AE * fv[c] : vfma(AE, fv[c], gLN0);
+        }
+        shade_bwd<T, NC>(g, px, f, gf, gLN0, acc);
     }
 }
 
 template <typename T, int C, typename IO>
 SVB_DEV void render_bwd_channel_pass(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N,
-                                     const float* __restrict__ gin, size_t HW, T (&g)[12]) {
+                                     const float* __restrict__ gin, size_t HW, T (&g)[12], IO& ring) {
     const Pix<T, 1> px = make_pix<T, 1>(&v[0], &v[3 + C], &v[9 + C], v[6 + C]);
     Acc<T, 1> acc;
     acc_zero(acc);
-    render_bwd_records<T, 1, C, IO>(px, x, y, rec, N, gin, HW, acc);
+    render_bwd_records<T, 1, C, IO>(px, x, y, rec, N, gin, HW, acc, ring);
+    T gd[1], gs[1];
+    acc_albedo_grads<T, 1>(acc, &v[3 + C], &v[9 + C], gd, gs);
 #pragma unroll
     for (int j = 0; j < 3; ++j) g[j] = g[j] + acc.gn[j];
-    g[3 + C] = acc.gd[0];
+    g[3 + C] = gd[0];
     g[6 + C] = acc.ga2[0] * rough_chain(v[6 + C]);
-    g[9 + C] = acc.gs[0];
+    g[9 + C] = gs[0];
 }
 
 // grad_maps of one thread's pixels: sum over records of J^T grad_images (autograd of renderers.py:67-104)
 template <typename T, typename IO>
 SVB_DEV void render_bwd_pixel(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N,
-                              const float* __restrict__ gin, size_t HW, T (&g)[12]) {
+                              const float* __restrict__ gin, size_t HW, T (&g)[12], IO& ring) {
     if (SVB_WARP_ALL(same3(v))) {
         const Pix<T, 3> px = make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]);
         Acc<T, 3> acc;
         acc_zero(acc);
-        render_bwd_records<T, 3, 0, IO>(px, x, y, rec, N, gin, HW, acc);
+        render_bwd_records<T, 3, 0, IO>(px, x, y, rec, N, gin, HW, acc, ring);
         const T chain = rough_chain(v[6]);
+        T gd[3], gs[3];
+        acc_albedo_grads<T, 3>(acc, &v[3], &v[9], gd, gs);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             g[c] = acc.gn[c];
-            g[3 + c] = acc.gd[c];
+            g[3 + c] = gd[c];
             g[6 + c] = acc.ga2[c] * chain;
-            g[9 + c] = acc.gs[c];
+            g[9 + c] = gs[c];
         }
     } else {
         g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f);
-        render_bwd_channel_pass<T, 0, IO>(v, x, y, rec, N, gin, HW, g);
-        render_bwd_channel_pass<T, 1, IO>(v, x, y, rec, N, gin, HW, g);
-        render_bwd_channel_pass<T, 2, IO>(v, x, y, rec, N, gin, HW, g);
+        render_bwd_channel_pass<T, 0, IO>(v, x, y, rec, N, gin, HW, g, ring);
+        render_bwd_channel_pass<T, 1, IO>(v, x, y, rec, N, gin, HW, g, ring);
+        render_bwd_channel_pass<T, 2, IO>(v, x, y, rec, N, gin, HW, g, ring);
     }
 }
 

@@ -61,7 +61,9 @@ SVB_DEV float mufu_noise(float v) { return v; }
 SVB_DEV float mufu_rcp(float x) { return mufu_noise(1.0f / x); }
 SVB_DEV float mufu_rsqrt(float x) { return mufu_noise(1.0f / sqrtf(x)); }
 SVB_DEV float mufu_lg2(float x) { return log2f(x); }
+SVB_DEV float mufu_sqrt(float x) { return mufu_noise(sqrtf(x)); }
 #else
+SVB_DEV float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 SVB_DEV float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 SVB_DEV float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 SVB_DEV float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -103,15 +105,30 @@ struct B2 { bool x, y; };
 SVB_DEV float vneg(float a) { return -a; }
 SVB_DEV F2 vneg(F2 a) { return mk2(-lo(a), -hi(a)); }
 SVB_DEV float vmax(float a, float m) { return fmaxf(a, m); }
+#ifdef SVB_ABL_NOMINMAX  // timing ablation only (wrong results)
+SVB_DEV F2 vmax(F2 a, float m) { return a; }
+#else
 SVB_DEV F2 vmax(F2 a, float m) { return mk2(fmaxf(lo(a), m), fmaxf(hi(a), m)); }
+#endif
+SVB_DEV float vmin(float a, float m) { return fminf(a, m); }
+SVB_DEV F2 vmin(F2 a, float m) { return mk2(fminf(lo(a), m), fminf(hi(a), m)); }
 SVB_DEV float vabs(float a) { return fabsf(a); }
 SVB_DEV F2 vabs(F2 a) { return mk2(fabsf(lo(a)), fabsf(hi(a))); }
-SVB_DEV float vrcp(float a) { return mufu_rcp(a); }
+#ifdef SVB_ABL_NOMUFU   // timing ablation only (wrong results): every MUFU pair becomes one packed multiply
+SVB_DEV F2 operator*(F2 a, F2 b);
+SVB_DEV F2 vrcp(F2 a) { return a * mk2(1.0009765625f, 1.0009765625f); }
+SVB_DEV F2 vrsqrt(F2 a) { return a * mk2(0.9990234375f, 0.9990234375f); }
+SVB_DEV F2 vlg2(F2 a) { return a * mk2(1.0029296875f, 1.0029296875f); }
+#else
 SVB_DEV F2 vrcp(F2 a) { return mk2(mufu_rcp(lo(a)), mufu_rcp(hi(a))); }
-SVB_DEV float vrsqrt(float a) { return mufu_rsqrt(a); }
 SVB_DEV F2 vrsqrt(F2 a) { return mk2(mufu_rsqrt(lo(a)), mufu_rsqrt(hi(a))); }
-SVB_DEV float vlg2(float a) { return mufu_lg2(a); }
 SVB_DEV F2 vlg2(F2 a) { return mk2(mufu_lg2(lo(a)), mufu_lg2(hi(a))); }
+#endif
+SVB_DEV float vsqrt(float a) { return mufu_sqrt(a); }
+SVB_DEV F2 vsqrt(F2 a) { return mk2(mufu_sqrt(lo(a)), mufu_sqrt(hi(a))); }
+SVB_DEV float vrcp(float a) { return mufu_rcp(a); }
+SVB_DEV float vrsqrt(float a) { return mufu_rsqrt(a); }
+SVB_DEV float vlg2(float a) { return mufu_lg2(a); }
 SVB_DEV bool vge(float a, float b) { return a >= b; }
 SVB_DEV B2 vge(F2 a, float b) { return B2{lo(a) >= b, hi(a) >= b}; }
 SVB_DEV float vsel(bool m, float a, float b) { return m ? a : b; }
@@ -174,8 +191,9 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
     const T hx = g.wix + g.wox, hy = g.wiy + g.woy, hz = g.wiz + g.woz;
     const T hh = vfma(hx, hx, vfma(hy, hy, hz * hz));
     g.ih = vrsqrt(hh);       // (a Newton step here was measured on B200: no accuracy gain, the residual error is fp32 rounding of n.h itself)
-    const T vh = vmax((hh * g.ih) * 0.5f, kClamp);          // wo.h = |wi+wo|/2 for unit vectors, clamped (renderers.py:49)
-    const T m = 1.f - vh, m2 = m * m;
+    // wo.h = |wi+wo|/2 for unit vectors, clamped at 1e-3 (renderers.py:49); 1 - max(t/2, c) = min(1 - t/2, 1 - c),
+    // bit-identical (t/2 is exact) and one packed operation shorter
+    const T m = vmin(vfma(hh * g.ih, -0.5f, 1.f), 1.f - kClamp), m2 = m * m;
     g.p5 = (m2 * m2) * m;
     g.omp5 = 1.f - g.p5;
     return g;
@@ -185,11 +203,16 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
 // Scaling convention: everything below works with f' = pi * f (BRDF value times pi) so that the
 // diffuse albedo enters unscaled and 1/pi is folded into the light term E' = colour * falloff / pi,
 // which is warp-uniform (one multiply per record instead of per pixel and map).
+//
+// BRDF blend (renderers.py:18-20,29-32,62-65).  With F = s + (1-s) p5 = s (1-p5) + p5:
+//     f' = (1-F) d + F S = (1-p5) * (d (1-s) + s S) + p5 * S
+// - a sum of non-negative terms (no cancellation even where F ~ 1e-3 multiplies S ~ 1e4), and per record
+// and channel only two fused operations on the per-pixel constants s and dk = d (1-s).
 template <typename T, int NC>
 struct Pix {
     T nx, ny, nz;      // normal, used as given (not re-normalised; renderers.py:84)
-    T d[NC];           // diffuse albedo                      (renderers.py:18-20)
     T s[NC];           // specular albedo
+    T dk[NC];          // diffuse albedo * (1 - specular albedo)
     T a2;              // alpha^2 = clamp(rough,1e-3)^4       (renderers.py:23-24,87)
     T oma2;            // 1 - alpha^2
 };
@@ -200,7 +223,7 @@ SVB_DEV Pix<T, NC> make_pix(const T* n, const T* d, const T* s, T rough) {
     Pix<T, NC> p;
     p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { p.d[c] = d[c]; p.s[c] = s[c]; }
+    for (int c = 0; c < NC; ++c) { p.s[c] = s[c]; p.dk[c] = d[c] * (1.f - s[c]); }
     const T r = vmax(rough, kClamp);
     const T a = r * r;
     p.a2 = a * a;
@@ -209,7 +232,7 @@ SVB_DEV Pix<T, NC> make_pix(const T* n, const T* d, const T* s, T rough) {
 }
 
 // ---- forward shading of one map under one scene record -----------------------------------------
-template <typename T, int NC>
+template <typename T>
 struct Fwd {
     T NHr, VNr, LNr;       // unclamped dots (for the clamp masks)
     T NH, VN, LN, LN0;
@@ -219,11 +242,11 @@ struct Fwd {
     T wV, wL;
     T iR;                  // 1 / (q^2 (VN+wV)(LN+wL))
     T S;                   // pi * G D / (4 VN LN) = a2 * iR
-    T F[NC], f[NC], Smd[NC];    // Fresnel, pi * BRDF value, S - d
 };
 
+// Everything of the specular lobe that is shared by the colour channels.
 template <typename T, int NC, bool BWD>
-SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T, NC>& o) {
+SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T>& o) {
     o.LNr = vfma(p.nx, g.wix, vfma(p.ny, g.wiy, p.nz * g.wiz));
     o.VNr = vfma(p.nx, g.wox, vfma(p.ny, g.woy, p.nz * g.woz));
     o.NHr = (o.LNr + o.VNr) * g.ih;
@@ -234,29 +257,46 @@ SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T, NC>& o) {
     const T qc = vmax(o.q, kClamp);
     const T tV = vfma(o.VN2, p.oma2, p.a2);
     const T tL = vfma(o.LN2, p.oma2, p.a2);
-    const T rwV = vrsqrt(tV), rwL = vrsqrt(tL);
-    o.wV = tV * rwV; o.wL = tL * rwL;
-    const T PV = o.VN + o.wV, PL = o.LN + o.wL;
-    if (BWD) {
+    if (!BWD) {
+        // forward only: sqrt is one MUFU operation; the backward also needs 1/sqrt, so there rsqrt and a multiply
+        o.wV = vsqrt(tV); o.wL = vsqrt(tL);
+        o.iR = vrcp((qc * qc) * ((o.VN + o.wV) * (o.LN + o.wL)));
+    } else {
+        const T rwV = vrsqrt(tV), rwL = vrsqrt(tL);
+        o.wV = tV * rwV; o.wL = tL * rwL;
+        const T PV = o.VN + o.wV, PL = o.LN + o.wL;
         const T iq = vrcp(qc), iPV = vrcp(PV), iPL = vrcp(PL);
         o.iq = iq; o.zV = rwV * iPV; o.zL = rwL * iPL;
         o.iR = (iq * iq) * (iPV * iPL);
-    } else {
-        o.iR = vrcp((qc * qc) * (PV * PL));
     }
     o.S = p.a2 * o.iR;
+}
+
+// pi * BRDF value of the NC channels (see Pix): f'_c = (1-p5) (dk_c + s_c S) + p5 S
+template <typename T, int NC>
+SVB_DEV void brdf_values(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T>& o, T (&f)[NC]) {
+    const T p5S = g.p5 * o.S;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        o.F[c] = vfma(p.s[c], g.omp5, g.p5);                      // s + (1-s)(1-VH)^5 (renderers.py:32)
-        o.Smd[c] = o.S - p.d[c];
-        o.f[c] = vfma(o.F[c], o.Smd[c], p.d[c]);                  // (1-F) d + F S      (renderers.py:62-65, times pi)
-    }
+    for (int c = 0; c < NC; ++c) f[c] = vfma(g.omp5, vfma(o.S, p.s[c], p.dk[c]), p5S);
+}
+
+// EL * f'_c + eps for a light term EL shared by the channels (grey light), without forming f':
+//   eps + EL p5 S + (EL (1-p5)) (dk_c + s_c S)
+template <typename T, int NC>
+SVB_DEV void radiance_plus_eps_grey(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T>& o, T EL, float eps, T (&x)[NC]) {
+    const T ELo = EL * g.omp5;
+    const T c0 = vfma(EL * o.S, g.p5, eps);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) x[c] = vfma(ELo, vfma(o.S, p.s[c], p.dk[c]), c0);
 }
 
 // ---- gradient accumulators of one pixel (summed over scene records) ----------------------------
+// U_c = sum gf_c (1-p5) and W_c = sum gf_c (1-p5) S with gf_c = d loss / d f'_c: the diffuse and specular
+// albedo gradients are assembled from them once per pixel (acc_albedo_grads), because
+// d f'_c / d d_c = (1-p5)(1-s_c) and d f'_c / d s_c = (1-p5)(S - d_c) only involve per-pixel constants besides.
 template <typename T, int NC>
 struct Acc {
-    T gn[3], gd[NC], gs[NC], ga2[NC];
+    T gn[3], U[NC], W[NC], ga2[NC];
 };
 template <typename T, int NC>
 SVB_DEV void acc_zero(Acc<T, NC>& a) {
@@ -264,15 +304,24 @@ SVB_DEV void acc_zero(Acc<T, NC>& a) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) a.gn[c] = z;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { a.gd[c] = z; a.gs[c] = z; a.ga2[c] = z; }
+    for (int c = 0; c < NC; ++c) { a.U[c] = z; a.W[c] = z; a.ga2[c] = z; }
+}
+// d loss / d diffuse_c and d loss / d specular_c from the accumulators (d, s: the pixel's albedo channels)
+template <typename T, int NC>
+SVB_DEV void acc_albedo_grads(const Acc<T, NC>& a, const T* d, const T* s, T (&gd)[NC], T (&gs)[NC]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        gd[c] = a.U[c] * (1.f - s[c]);
+        gs[c] = a.W[c] - d[c] * a.U[c];
+    }
 }
 
-// AE[c] = (d loss / d radiance_c) * E'_c for this (pixel, record), E'_c = light colour_c * falloff / pi.
-// Adds the adjoint of shade_fwd and of the radiance product (renderers.py:96-100) into acc.
+// gf[c] = d loss / d f'_c and gLN0 = d loss / d LN0 (through the radiance product, renderers.py:96-100)
+// for this (pixel, record).  Adds the adjoint of shade_fwd / brdf_values into acc.
 // Clamp masks are applied as 0/1 (or 0/2) float factors: one compare-and-set per lane plus a packed
 // multiply is cheaper in register-file cycles than predicated moves of register pairs.
 template <typename T, int NC>
-SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T, NC>& o, const T (&AE)[NC],
+SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T>& o, const T (&gf)[NC], T gLN0,
                        Acc<T, NC>& acc) {
     // w = 2 NH / q where the clamp on q passes (renderers.py:26), else 0
     const T w = (o.NH * o.iq) * vstep(o.q, kClamp, 2.f);
@@ -280,14 +329,13 @@ SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T, NC>& o
     const T hV = vfma(o.VN2, -0.5f, 0.5f), hL = vfma(o.LN2, -0.5f, 0.5f);
     const T rest = vfma(o.NH, w, vfma(hV, o.zV, hL * o.zL));
     const T Tk = o.iR - o.S * rest;
-    T gLN0, gFsum;
+    const T oS = g.omp5 * o.S;
+    T gFsum;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        const T gf = AE[c] * o.LN0;
-        gLN0 = (c == 0) ? AE[c] * o.f[c] : vfma(AE[c], o.f[c], gLN0);
-        const T gfF = gf * o.F[c];
-        acc.gd[c] = (acc.gd[c] + gf) - gfF;                       // += gf (1 - F): two 2-operand adds beat sub + 3-operand fma
-        acc.gs[c] = vfma(gf * o.Smd[c], g.omp5, acc.gs[c]);
+        acc.U[c] = vfma(gf[c], g.omp5, acc.U[c]);
+        acc.W[c] = vfma(gf[c], oS, acc.W[c]);
+        const T gfF = gf[c] * vfma(p.s[c], g.omp5, g.p5);         // gf * F, F = s + (1-s)(1-VH)^5 (renderers.py:32)
         acc.ga2[c] = vfma(gfF, Tk, acc.ga2[c]);
         gFsum = (c == 0) ? gfF : gFsum + gfF;
     }

@@ -21,6 +21,24 @@ struct HostIO {
     static void st(float* p, F2 v) { p[0] = lo(v); p[1] = hi(v); }
 };
 
+// host stand-in of the kernels' RingIO (pixel_ops.cuh render_bwd_records): same fetch / skip / take protocol
+template <typename T>
+struct HostRing {
+    static constexpr int kDepth = 3, kSlots = 4;
+    T buf[kSlots][3];
+    int head, tail;
+    void reset() { head = tail = 0; }
+    template <int NC> void fetch(const float* p, size_t HW) {
+        for (int c = 0; c < NC; ++c) HostIO::ld(p + (size_t)c * HW, buf[head % kSlots][c]);
+        ++head;
+    }
+    void skip() { ++head; }
+    template <int NC> void take(T (&a)[NC]) {
+        for (int c = 0; c < NC; ++c) a[c] = buf[tail % kSlots][c];
+        ++tail;
+    }
+};
+
 bool all_grey(const float* recs, int nrec) {
     for (int i = 0; i < nrec; ++i) {
         const float* c = recs + (size_t)i * kRecFloats + 6;
@@ -85,7 +103,8 @@ void render_bwd_image(const float* maps, int W, size_t HW, const float* rec, int
         T v[12], g[12], x;
         for (int c = 0; c < 12; ++c) HostIO::ld(maps + c * HW + p, v[c]);
         HostIO::ld(lin + p % W, x);
-        render_bwd_pixel<T, HostIO>(v, x, -lin[p / W], rec, N, gimages + p, HW, g);
+        HostRing<T> ring;
+        render_bwd_pixel<T, HostRing<T>>(v, x, -lin[p / W], rec, N, gimages + p, HW, g, ring);
         for (int c = 0; c < 12; ++c) HostIO::st(gmaps + c * HW + p, g[c]);
     }
 }
