@@ -41,6 +41,9 @@ WORKLOADS = {
     "c5": (32, 256, 9, 3, 6, "configs[4] loss part: global batch 256 over 8 GPUs = 32 per GPU, 256x256, 9 configs"),
 }
 FLOP_PER_EVAL = 330.0        # SURVEY.md §8d canonical fwd+bwd count (FMA = 2)
+# Register-file operand-bandwidth model of the hot loop (scripts/sass_stats.py on the shipped kernel: cycles one
+# scheduler needs to fetch the operands of one record iteration of one warp = 64 pixels)
+RF_CYCLES_PER_WARP_RECORD = 440.0
 BYTES_PER_PIXEL = 144.0      # read input 48 + read target 48 + write grad 48
 METRIC = "rendering-loss fwd+bwd pixel-light evals/s"
 UNIT = "G evals/s"
@@ -391,6 +394,13 @@ def run_ours(args):
                 "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": evals_per_step, "kernel_ms": kernel_ms,
                 "G_evals_per_s_kernel": evals_per_step / (kernel_ms * 1e-3) / 1e9,
                 "G_evals_per_s_at_100pct": nominal_fp32 * 1e12 / FLOP_PER_EVAL / 1e9}
+    # the bound that actually binds: operand fetch from the two register-file banks of each scheduler
+    warp_records = B * HW * N / 64.0
+    rf_ms = RF_CYCLES_PER_WARP_RECORD * warp_records / (sms * 4) / (sm_max_mhz * 1e6) * 1e3
+    roofline_rf = {"bound": "register-file operand bandwidth (model)", "cycles_per_warp_record": RF_CYCLES_PER_WARP_RECORD,
+                   "bound_ms": rf_ms, "frac": rf_ms / kernel_ms,
+                   "how": "scripts/sass_stats.py cost model (B300_MICROARCH.md 'RF banking': rt = max(pipe, distinct even, distinct odd source registers)) "
+                          "x warp-record iterations / (SMs x 4 schedulers x SM clock); prologue/epilogue not counted"}
     roofline_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
                     "frac": ach_gbs / float(peaks["hbm_gbs"]), "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs",
                     "bytes_per_pixel": BYTES_PER_PIXEL, "traffic": traffic}
@@ -419,7 +429,7 @@ def run_ours(args):
                        "l2": "2 rotating buffer sets; each set (input+target+grad) is %.0f MB > 126 MB L2" % (3 * B * 12 * HW * 4 / 1e6),
                        "scene_sampler_ms_per_step_host": sampler_ms},
             "value_per_gpu": value / world, "loss": loss_value,
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "fp32_probes_tflops": probes,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_register_file": roofline_rf, "fp32_probes_tflops": probes,
             "cpu_baseline": cpu, "reference_port_eager_on_gpu": eager, "e2e": e2e, "gpu_launches": 2 * steps,
             "gpu_launches_note": "per step: 1 fused loss fwd+bwd kernel + 1 single-CTA finalize kernel",
             "clocks": sampler.summary(clock_note),

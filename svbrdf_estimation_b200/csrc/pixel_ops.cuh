@@ -192,24 +192,25 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
 // unscaled sum); adds their gradient, scaled by `scale`, to g.
 template <typename T, bool BWD>
 SVB_DEV T l1_pixel(const T (&vi)[12], const T (&vt)[12], float scale, T (&g)[12]) {
-    T s = LaneTraits<T>::splat(0.f);
+    T s_lin = LaneTraits<T>::splat(0.f), s_lg2 = LaneTraits<T>::splat(0.f);
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
         const bool logged = (c >= 3 && c < 6) || c >= 9;      // diffuse and specular use log(x + 0.01)
         const T diff = vi[c] - vt[c];                         // sign(log a' - log b') = sign(a - b), exact at 0
         if (logged) {
-            // |log a' - log b'| as one lg2 of the ratio; 1/a' is also d log(a')/da.  (This block runs once per
-            // pixel, but its MUFU burst is as long as a whole record iteration, so every MUFU saved here counts.)
+            // |log a' - log b'| = |lg2(b'/a')| ln2 with b'/a' = 1 - (a - b)/a': exactly 1 (and the log exactly 0) for
+            // identical values, and 1/a' is also d log(a')/da.  (This block runs once per pixel, but it is as long as a
+            // record iteration, so every instruction saved here counts for MixedLoss.)
             const T ra = vrcp(vi[c] + kEpsL1);
-            const T l = vlg2((vt[c] + kEpsL1) * ra);
-            s = s + vnonzero(diff, vabs(l) * kLn2);
-            if (BWD) g[c] = g[c] + vsigned(diff, ra * scale);
+            const T l = vlg2(vfma(vneg(diff), ra, 1.f));
+            s_lg2 = s_lg2 + vabs(l);
+            if (BWD) g[c] = g[c] + vsignz(diff, ra * scale);
         } else {
-            s = s + vabs(diff);
-            if (BWD) g[c] = g[c] + vsigned(diff, LaneTraits<T>::splat(scale));
+            s_lin = s_lin + vabs(diff);
+            if (BWD) g[c] = g[c] + vsignz(diff, LaneTraits<T>::splat(scale));
         }
     }
-    return s;
+    return vfma(s_lg2, kLn2, s_lin);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -136,6 +136,9 @@ SVB_DEV F2 vsel(B2 m, F2 a, float b) { return mk2(m.x ? lo(a) : b, m.y ? hi(a) :
 // sign(d) * v with sign(0) = 0 (torch.sign / l1_loss backward)
 SVB_DEV float vsigned(float d, float v) { return (d > 0.f) ? v : ((d < 0.f) ? -v : 0.f); }
 SVB_DEV F2 vsigned(F2 d, F2 v) { return mk2(vsigned(lo(d), lo(v)), vsigned(hi(d), hi(v))); }
+// sign(d) * v for v >= 0, sign(0) = 0: copysign + one compare-select per lane
+SVB_DEV float vsignz(float d, float v) { return d != 0.f ? copysignf(v, d) : 0.f; }
+SVB_DEV F2 vsignz(F2 d, F2 v) { return mk2(vsignz(lo(d), lo(v)), vsignz(hi(d), hi(v))); }
 // |v| with the sign of d (one LOP3 per lane); d == 0 counts as positive - used where an exact zero of d
 // is handled separately (see loss_kernel: bitwise-identical inputs are masked per pixel / per channel)
 SVB_DEV float vcopysign(float v, float d) { return copysignf(v, d); }
