@@ -133,6 +133,23 @@ def test_render_backward_vs_oracle_autograd(S):
     parity.check_grad_groups(x.grad.cpu().numpy(), m32.grad.numpy(), m64.grad.numpy(), "render_bwd", rel=parity.REL_L2_RAW_RENDER_GRAD)
 
 
+@pytest.mark.parametrize("n_records", [2, 3, 4, 7])
+@pytest.mark.parametrize("size", [18, 15])
+def test_render_backward_record_ring(S, n_records, size):
+    """The upstream gradient streams through a per-thread cp.async ring (3 records in flight): record counts below,
+    at and above the ring depth, packed (even width) and one-pixel-per-thread (odd width) kernels."""
+    maps = synthetic_maps(2, size, 61 + n_records)
+    torch.manual_seed(9)
+    cfg = O.sample_loss_configs(2, n_records - 1, 1)
+    w = torch.randn(2, n_records, 3, size, size)
+    m64 = maps.double().requires_grad_(True)
+    (O.render_batch(m64, cfg) * w.double()).sum().backward()
+    x = maps.cuda().requires_grad_(True)
+    (S.render_records(x, cfg) * w.cuda()).sum().backward()
+    for name, s in parity.GROUPS:
+        assert parity.rel_l2(x.grad.cpu().numpy()[:, s], m64.grad.numpy()[:, s]) <= parity.REL_L2_RAW_RENDER_GRAD, name
+
+
 def test_fixed_scene_loss_through_render_autograd(S):
     """Notebook-style loss (website.ipynb cell 15): plain L1 between renders, autograd through render()."""
     maps, tgt = synthetic_maps(1, 32, 41), synthetic_maps(1, 32, 42)
