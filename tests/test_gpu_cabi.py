@@ -1,6 +1,7 @@
 """The C ABI called directly (ctypes, raw device pointers) and size-independent properties at the
 BASELINE.json sizes.  Needs a GPU: ``pytest -m gpu``."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -181,3 +182,35 @@ def test_work_is_enqueued_on_the_callers_stream(env):
         got = S.rendering_loss_with_records(inp, tgt, rec)
     s.synchronize()
     assert float(got) == float(ref)
+
+
+def test_plain_c_program_through_the_host_entry(env, tmp_path):
+    """examples/c_abi_demo.c (gcc, include/svbrdf_b200.h + the .so only, no PyTorch in the process) computes the same loss
+    and the bit-identical gradient as the Python layer on the inputs it writes out."""
+    import shutil
+    import subprocess
+    import numpy as np
+    import svbrdf_estimation_b200 as S
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "svbrdf_estimation_b200")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_demo.c"),
+                           "-o", exe, "-L" + pkg, "-lsvbrdf_b200", "-Wl,-rpath," + pkg, "-lm"])
+    out = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    c_loss = float(out.stdout.split()[1])
+    B, N, H, W = 3, 9, 40, 40
+    load = lambda name, shape: torch.from_numpy(np.fromfile(str(tmp_path / name), dtype=np.float32).reshape(shape).copy())
+    inp, tgt = load("input.f32", (B, 12, H, W)), load("target.f32", (B, 12, H, W))
+    rec, c_grad = load("records.f32", (B, N, 9)), load("grad.f32", (B, 12, H, W))
+    x = inp.cuda().requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, tgt.cuda(), rec)
+    loss.backward()
+    assert abs(float(loss) - c_loss) <= 1e-6 * c_loss
+    assert torch.equal(x.grad.cpu(), c_grad)
+    from oracle import reference_port as O                      # and both agree with the reference's math
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), rec)
+    assert abs(c_loss - float(l64)) <= 2e-6 * float(l64)
+    assert float((c_grad.double() - g64).norm() / g64.norm()) <= 1.5e-4
