@@ -428,9 +428,9 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, sec, b, threads = time_cpu_port(args.workload, 5, 1, budget_s=40.0)
+        val, sec, b, threads = time_cpu_port(args.workload, 15, 1, budget_s=40.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "first %d of %d maps of the workload, %dx%d, N=%d, 1 warm-up + 5 timed fwd+bwd passes (%.2f s each)"
+               "sample": "first %d of %d maps of the workload, %dx%d, N=%d, 1 warm-up + 15 timed fwd+bwd passes (%.2f s each)"
                          % (b, B, size, size, N, sec)}
 
     eager = None
