@@ -7,7 +7,7 @@ mkdir -p $O
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,pcie.link.gen.current,pcie.link.width.current --format=csv > $O/gpu.txt
 python -m pytest tests -m gpu -q 2>&1 | tail -2 > $O/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
-python scripts/parity_report.py > $O/parity.json 2> $O/parity.err
+python scripts/parity_report.py --full > $O/parity.json 2> $O/parity.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err
 python bench.py --steps 200 --warmup 5 > $O/bench_c2.json 2> $O/bench_c2.err
 for w in c1 c3 c4 c5; do python bench.py --workload $w --steps 100 --warmup 5 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err; done

@@ -26,15 +26,32 @@ def ours(inp, tgt, cfg):
     return float(loss.detach()), x.grad.cpu().numpy(), renders
 
 
-def report(name, inp, tgt, cfg, l32, g32, r32, l64, g64, r64):
+AMBIGUOUS_DLOG = 1e-3     # |log difference| below which fp32 cannot be expected to get the SIGN of an L1 term right
+
+
+def report(name, inp, tgt, cfg, l32, g32, r32, l64, g64, r64, r64_target=None):
+    """r64_target (fp64 renders of the target maps) enables the sign-ambiguity analysis: the loss is an L1 of log
+    renders, so d loss / d render = sign(l) / M; where the two renders agree to |l| < 1e-3 (but are not identical) an
+    fp32 evaluation - the reference's own included - may pick the other sign, which flips that term's whole
+    gradient.  One such term on a highlight pixel can carry the entire rel-L2 of a gradient group, so the groups are
+    also reported over the pixels that have no such term."""
     loss, grad, renders = ours(inp, tgt, cfg)
     row = {"case": name, "shape": list(np.shape(inp)), "N": int(np.shape(cfg)[1]),
            "loss_rel_err_vs_ref64": abs(loss - float(l64)) / abs(float(l64)),
            "ref32_loss_rel_err_vs_ref64": abs(float(l32) - float(l64)) / abs(float(l64))}
+    keep = None
+    if r64_target is not None:
+        l = np.abs(np.log(r64 + 0.1) - np.log(r64_target + 0.1))               # [B,N,3,H,W]
+        amb = ((l > 0) & (l < AMBIGUOUS_DLOG)).any(axis=(1, 2))                # [B,H,W]
+        keep = ~amb[:, None]
+        row["sign_ambiguous_pixels"] = {"count": int(amb.sum()), "fraction": float(amb.mean()), "threshold_dlog": AMBIGUOUS_DLOG}
     for gname, s in parity.GROUPS:
         row["grad_" + gname] = {"ours_vs_ref32": parity.rel_l2(grad[:, s], g32[:, s]),
                                 "ours_vs_ref64": parity.rel_l2(grad[:, s], g64[:, s]),
                                 "ref32_vs_ref64": parity.rel_l2(g32[:, s], g64[:, s])}
+        if keep is not None:
+            row["grad_" + gname].update({"ours_vs_ref64_unambiguous": parity.rel_l2(grad[:, s] * keep, g64[:, s] * keep),
+                                         "ref32_vs_ref64_unambiguous": parity.rel_l2(g32[:, s] * keep, g64[:, s] * keep)})
     if r64 is not None:
         rel = np.abs(renders - r64) / np.maximum(np.abs(r64), 1e-30)
         relr = np.abs(r32 - r64) / np.maximum(np.abs(r64), 1e-30)
@@ -50,7 +67,7 @@ def report(name, inp, tgt, cfg, l32, g32, r32, l64, g64, r64):
 def main():
     rows = []
     gdir = os.path.join(ROOT, "tests", "golden")
-    for fx in ("loss_bench", "loss_stress", "loss_n27"):
+    for fx in ("loss_bench", "loss_stress", "loss_n27", "loss_real"):
         g = dict(np.load(os.path.join(gdir, fx + ".npz")))
         rows.append(report("golden:" + fx, g["input"], g["target"], g["configs"], g["loss_f32"], g["grad_f32"],
                            g.get("renders_f32"), g["loss_f64"], g["grad_f64"], g.get("renders_f64")))
@@ -62,7 +79,24 @@ def main():
         l32, g32 = O.rendering_loss_and_grad(inp, tgt, cfg)
         r64, r32 = O.render_batch(inp.double(), cfg).numpy(), O.render_batch(inp, cfg).numpy()
         rows.append(report("oracle:%dx%d B%d%s" % (size, size, batch, " stress" if stress else ""), inp.numpy(), tgt.numpy(),
-                           cfg.numpy(), l32, g32.numpy(), r32, l64, g64.numpy(), r64))
+                           cfg.numpy(), l32, g32.numpy(), r32, l64, g64.numpy(), r64, O.render_batch(tgt.double(), cfg).numpy()))
+    if "--full" in sys.argv:
+        # BASELINE.json shapes at full resolution: the oracle itself runs on the GPU here (same eager code, fp64 = ground
+        # truth, fp32 = what the reference computes), in batch slices that fit its autograd graph
+        for name, batch, size, nr, ns in (("C1 shape 256x256 B8 N9", 8, 256, 3, 6), ("C3 records 256x256 B4 N27", 4, 256, 9, 18),
+                                          ("C4 resolution 1024x1024 B1 N9", 1, 1024, 3, 6)):
+            inp, tgt = synthetic_maps(batch, size, 21), synthetic_maps(batch, size, 22)
+            torch.manual_seed(313)
+            cfg = O.sample_loss_configs(batch, nr, ns)
+            dev = torch.device("cuda", 0)
+            l64, g64 = O.rendering_loss_and_grad(inp.double().to(dev), tgt.double().to(dev), cfg)
+            l32, g32 = O.rendering_loss_and_grad(inp.to(dev), tgt.to(dev), cfg)
+            with torch.no_grad():
+                r64, r32 = O.render_batch(inp.double().to(dev), cfg).cpu().numpy(), O.render_batch(inp.to(dev), cfg).cpu().numpy()
+                r64t = O.render_batch(tgt.double().to(dev), cfg).cpu().numpy()
+            rows.append(report("oracle-on-gpu:" + name, inp.numpy(), tgt.numpy(), cfg.numpy(), float(l32), g32.cpu().numpy(), r32,
+                               float(l64), g64.cpu().numpy(), r64, r64t))
+            torch.cuda.empty_cache()
     print(json.dumps(rows, indent=1))
 
 

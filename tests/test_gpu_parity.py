@@ -409,3 +409,26 @@ def test_dataset_input_synthesis_matches_reference(S, golden):
             np.testing.assert_allclose(got.cpu().numpy(), g["inputs_" + tag], rtol=2e-4, atol=2e-5)
     fast = I.render_inputs(torch.from_numpy(g["svbrdf"]).cuda(), 4, use_augmentation=True, noise="device")
     assert fast.shape == (4, 3, 16, 16) and float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0
+
+
+@pytest.mark.parametrize("shape", [(4, 256, 3, 6), (2, 256, 9, 18)])
+def test_full_resolution_gradient_parity(S, shape):
+    """BASELINE.json shapes at full resolution (256x256, N = 9 and N = 27): the oracle runs on the GPU in fp64 for the
+    ground truth.  Gradients are compared over the pixels without a sign-ambiguous L1 term (tests/parity.py)."""
+    batch, size, nr, ns = shape
+    dev = torch.device("cuda", 0)
+    inp, tgt = synthetic_maps(batch, size, 21), synthetic_maps(batch, size, 22)
+    torch.manual_seed(313)
+    cfg = O.sample_loss_configs(batch, nr, ns)
+    l64, g64 = O.rendering_loss_and_grad(inp.double().to(dev), tgt.double().to(dev), cfg)
+    with torch.no_grad():
+        keep = parity.unambiguous_pixels(O.render_batch(inp.double().to(dev), cfg).cpu().numpy(),
+                                         O.render_batch(tgt.double().to(dev), cfg).cpu().numpy())
+    x = inp.to(dev).requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, tgt.to(dev), cfg)
+    loss.backward()
+    parity.check_loss(float(loss), float(l64))
+    assert keep.mean() >= 0.9, "too many sign-ambiguous pixels: %.3f" % (1 - keep.mean())
+    g, g64 = x.grad.cpu().numpy(), g64.cpu().numpy()
+    for name, s in parity.GROUPS:
+        assert parity.rel_l2(g[:, s] * keep, g64[:, s] * keep) <= parity.REL_L2, name
