@@ -8,7 +8,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsvbrdf_b200.so")
+# SVBRDF_B200_LIB points at an alternative build of the same ABI (variant builds of scripts/variant_bench.py)
+LIB_PATH = os.environ.get("SVBRDF_B200_LIB") or os.path.join(_PKG, "libsvbrdf_b200.so")
 
 E_INVALID, E_TOO_LARGE, E_STATE = -1, -2, -3
 
