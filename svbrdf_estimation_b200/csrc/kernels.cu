@@ -241,7 +241,7 @@ struct DeviceIO {
     template <typename T> static __device__ __forceinline__ void st(float* p, T v) { st_stream(p, v); }
 };
 
-template <typename T, int CAP>
+template <typename T, int CAP, bool GREY>
 __global__ void __launch_bounds__(Cfg<T>::kThreads)
 render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     const int b = blockIdx.y;
@@ -250,7 +250,7 @@ render_fwd_kernel(const RenderArgs a, const __grid_constant__ SceneBlock<CAP> sc
     load12<T>(a.maps + (size_t)b * 12 * a.HW + w.p, a.HW, v);
     const float* rec = sc.v + (a.per_batch ? (size_t)b * a.N * kRecFloats : 0);
     float* out = a.images + (size_t)b * a.N * 3 * a.HW + w.p;
-    render_pixel<T, DeviceIO>(v, w.x, w.y, rec, a.N, out, (size_t)a.HW, w.live);
+    render_pixel<T, GREY, DeviceIO>(v, w.x, w.y, rec, a.N, out, (size_t)a.HW, w.live);
 }
 
 // Per-thread ring of upstream-gradient records in shared memory, filled with cp.async (LDGSTS): kDepth records
@@ -571,8 +571,11 @@ static cudaError_t launch_render_t(bool backward, bool small, dim3 grid, const R
     if (backward)
         return small ? launch_with_scenes<kCapSmall, TH>(render_bwd_kernel<T, kCapSmall>, grid, a, recs, nrec, st)
                      : launch_with_scenes<kCapLarge, TH>(render_bwd_kernel<T, kCapLarge>, grid, a, recs, nrec, st);
-    return small ? launch_with_scenes<kCapSmall, TH>(render_fwd_kernel<T, kCapSmall>, grid, a, recs, nrec, st)
-                 : launch_with_scenes<kCapLarge, TH>(render_fwd_kernel<T, kCapLarge>, grid, a, recs, nrec, st);
+    if (all_grey(recs, nrec))
+        return small ? launch_with_scenes<kCapSmall, TH>(render_fwd_kernel<T, kCapSmall, true>, grid, a, recs, nrec, st)
+                     : launch_with_scenes<kCapLarge, TH>(render_fwd_kernel<T, kCapLarge, true>, grid, a, recs, nrec, st);
+    return small ? launch_with_scenes<kCapSmall, TH>(render_fwd_kernel<T, kCapSmall, false>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, TH>(render_fwd_kernel<T, kCapLarge, false>, grid, a, recs, nrec, st);
 }
 
 static int render_impl(const float* maps, int B, int H, int W, const float* scenes, int N, int per_batch,

@@ -59,8 +59,13 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
         const float* __restrict__ rk = rec + k * kRecFloats;
         const Geo<T> g = make_geo<T>(x, y, rk);
         Fwd<T> fi, ft;
+#ifdef SVB_ACCURATE_LOSS       // build option: accurate-highlight forward in the loss kernels too (shading.cuh, ~ +13 % time)
+        shade_fwd<T, NC, BWD, true>(g, pi, fi);
+        shade_fwd<T, NC, false, true>(g, pt, ft);
+#else
         shade_fwd<T, NC, BWD>(g, pi, fi);
         shade_fwd<T, NC, false>(g, pt, ft);
+#endif
         // radiance + 0.1 of both maps (losses.py:46-47); E = light colour * falloff / pi
         T E[NC], fin[NC], xi[NC], xt[NC];
         if (GREY) {
@@ -251,33 +256,40 @@ SVB_DEV void encode_grad(const T (&v)[12], T inv_len, const T (&g)[12], T (&ge)[
 // LocalRenderer.render forward / backward
 // ---------------------------------------------------------------------------------------------
 // out points at this thread's pixel(s) in images[b,0,0]; records advance by 3*HW floats.
-template <typename T, int NC, int C0, typename IO>
+// GREY: every record has r == g == b light colour (all scenes the reference samples, environment.py:27,52; dataset.py
+// uses white lights too), so the radiance comes from the shared-light form without forming f' per channel.
+template <typename T, int NC, int C0, bool GREY, typename IO>
 SVB_DEV void render_records(const Pix<T, NC>& px, T x, float y, const float* __restrict__ rec, int N,
                             float* __restrict__ out, size_t HW, bool live) {
     SVB_UNROLL1
     for (int k = 0; k < N; ++k, rec += kRecFloats, out += 3 * HW) {
         const Geo<T> g = make_geo<T>(x, y, rec);
         Fwd<T> f;
-        shade_fwd<T, NC, false>(g, px, f);
-        T fv[NC];
-        brdf_values<T, NC>(g, px, f, fv);
+        shade_fwd<T, NC, false, true>(g, px, f);              // accurate-highlight form: the images are the product here
+        T rad[NC];                                             // renderers.py:100 (f' carries the factor pi)
+        if (GREY) {
+            radiance_plus_eps_grey<T, NC>(g, px, f, (g.fall * (rec[6 + C0] * kInvPi)) * f.LN0, 0.f, rad);
+        } else {
+            brdf_values<T, NC>(g, px, f, rad);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) rad[c] = rad[c] * ((g.fall * (rec[6 + C0 + c] * kInvPi)) * f.LN0);
+        }
         if (live) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c)   // renderers.py:100 (f' carries the factor pi)
-                IO::st(out + (size_t)(C0 + c) * HW, fv[c] * ((g.fall * (rec[6 + C0 + c] * kInvPi)) * f.LN0));
+            for (int c = 0; c < NC; ++c) IO::st(out + (size_t)(C0 + c) * HW, rad[c]);
         }
     }
 }
 
-template <typename T, typename IO>
+template <typename T, bool GREY, typename IO>
 SVB_DEV void render_pixel(const T (&v)[12], T x, float y, const float* __restrict__ rec, int N, float* __restrict__ out,
                           size_t HW, bool live) {
     if (SVB_WARP_ALL(same3(v))) {
-        render_records<T, 3, 0, IO>(make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
+        render_records<T, 3, 0, GREY, IO>(make_pix<T, 3>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
     } else {
-        render_records<T, 1, 0, IO>(make_pix<T, 1>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
-        render_records<T, 1, 1, IO>(make_pix<T, 1>(&v[0], &v[4], &v[10], v[7]), x, y, rec, N, out, HW, live);
-        render_records<T, 1, 2, IO>(make_pix<T, 1>(&v[0], &v[5], &v[11], v[8]), x, y, rec, N, out, HW, live);
+        render_records<T, 1, 0, GREY, IO>(make_pix<T, 1>(&v[0], &v[3], &v[9], v[6]), x, y, rec, N, out, HW, live);
+        render_records<T, 1, 1, GREY, IO>(make_pix<T, 1>(&v[0], &v[4], &v[10], v[7]), x, y, rec, N, out, HW, live);
+        render_records<T, 1, 2, GREY, IO>(make_pix<T, 1>(&v[0], &v[5], &v[11], v[8]), x, y, rec, N, out, HW, live);
     }
 }
 

@@ -172,6 +172,7 @@ struct Geo {
     T ih;              // 1 / |wi + wo|                      (renderers.py:45)
     T p5, omp5;        // (1-VH)^5 and its complement        (renderers.py:32,49)
     T fall;            // 1 / |light - p|^2                  (renderers.py:99)
+    T hx, hy, hz, ih2; // wi + wo and 1 / |wi + wo|^2 (only the accurate-highlight forward reads them)
 };
 
 // s points at one scene record (9 floats: camera xyz, light xyz, colour rgb) in the constant bank.
@@ -193,12 +194,14 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
     // (mirror configuration, n.wi ~ n.wo), which keeps the fp32 result near the reference's fp64 one.
     const T hx = g.wix + g.wox, hy = g.wiy + g.woy, hz = g.wiz + g.woz;
     const T hh = vfma(hx, hx, vfma(hy, hy, hz * hz));
+    g.hx = hx; g.hy = hy; g.hz = hz;
     g.ih = vrsqrt(hh);       // (a Newton step here was measured on B200: no accuracy gain, the residual error is fp32 rounding of n.h itself)
     // wo.h = |wi+wo|/2 for unit vectors, clamped at 1e-3 (renderers.py:49); 1 - max(t/2, c) = min(1 - t/2, 1 - c),
     // bit-identical (t/2 is exact) and one packed operation shorter
     const T m = vmin(vfma(hh * g.ih, -0.5f, 1.f), 1.f - kClamp), m2 = m * m;
     g.p5 = (m2 * m2) * m;
     g.omp5 = 1.f - g.p5;
+    g.ih2 = g.ih * g.ih;
     return g;
 }
 
@@ -218,6 +221,7 @@ struct Pix {
     T dk[NC];          // diffuse albedo * (1 - specular albedo)
     T a2;              // alpha^2 = clamp(rough,1e-3)^4       (renderers.py:23-24,87)
     T oma2;            // 1 - alpha^2
+    T omn2;            // 1 - |n|^2 to ~1e-8 absolute (only the accurate-highlight forward reads it)
 };
 
 // n[3] normals; d, s: NC diffuse / specular channels; rough: the roughness channel of this pass.
@@ -231,6 +235,12 @@ SVB_DEV Pix<T, NC> make_pix(const T* n, const T* d, const T* s, T rough) {
     const T a = r * r;
     p.a2 = a * a;
     p.oma2 = 1.f - p.a2;
+    {   // 1 - |n|^2 with the products' rounding errors recovered by FMA (exact residuals) and the dominant z term
+        // subtracted first (1 - nz^2 is exact for nz^2 in [0.5, 2], the case of every upper-hemisphere unit normal)
+        const T px = p.nx * p.nx, py = p.ny * p.ny, pz = p.nz * p.nz;
+        const T ex = vfma(p.nx, p.nx, vneg(px)), ey = vfma(p.ny, p.ny, vneg(py)), ez = vfma(p.nz, p.nz, vneg(pz));
+        p.omn2 = (((1.f - pz) - py) - px) - ((ex + ey) + ez);
+    }
     return p;
 }
 
@@ -248,7 +258,13 @@ struct Fwd {
 };
 
 // Everything of the specular lobe that is shared by the colour channels.
-template <typename T, int NC, bool BWD>
+// ACC (forward only): the GGX denominator q = 1 - NH^2 (1-a2) is where fp32 loses the highlights - NH^2 -> 1 and q -> a2,
+// so the ~1.5e-7 absolute rounding error of n.h = (n.wi+n.wo)/|wi+wo| becomes a relative error of up to 1e-3 in q and
+// twice that in D (the reference's own fp32 evaluation has the same problem, profiles/r1_accuracy_study.txt).  With
+// Lagrange's identity  1 - NH^2 = (1 - |n|^2) + |n x h|^2 / |h|^2,  h = wi + wo, the small quantity is computed from small
+// quantities (cross-product components ~ sqrt(1-NH^2), relative error ~1e-6) and a per-pixel constant: +10 packed
+// operations per map and record, used where the images themselves are the product (render_forward, HBM-bound anyway).
+template <typename T, int NC, bool BWD, bool ACC = false>
 SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T>& o) {
     o.LNr = vfma(p.nx, g.wix, vfma(p.ny, g.wiy, p.nz * g.wiz));
     o.VNr = vfma(p.nx, g.wox, vfma(p.ny, g.woy, p.nz * g.woz));
@@ -256,7 +272,19 @@ SVB_DEV void shade_fwd(const Geo<T>& g, const Pix<T, NC>& p, Fwd<T>& o) {
     o.NH = vmax(o.NHr, kClamp); o.VN = vmax(o.VNr, kClamp); o.LN = vmax(o.LNr, kClamp);
     o.LN0 = vmax(o.LNr, 0.f);                                     // renderers.py:96
     o.VN2 = o.VN * o.VN; o.LN2 = o.LN * o.LN;
-    o.q = 1.f - (o.NH * o.NH) * p.oma2;                           // NH^2 a2 + 1 - NH^2 (renderers.py:26)
+    if (ACC) {
+        const T cx = vfma(p.ny, g.hz, vneg(p.nz * g.hy)), cy = vfma(p.nz, g.hx, vneg(p.nx * g.hz)),
+                cz = vfma(p.nx, g.hy, vneg(p.ny * g.hx));
+        const T c2 = vfma(cx, cx, vfma(cy, cy, cz * cz));
+        const T om = vfma(c2, g.ih2, p.omn2);                                        // 1 - NHr^2
+        // clamp(n.h, min=1e-3) (renderers.py:48): below the bound NH^2 = 1e-6 whatever the raw value
+        const typename LaneTraits<T>::Mask live = vge(o.NHr, kClamp);
+        const T nh2 = vsel(live, 1.f - om, kClamp * kClamp);
+        const T omc = vsel(live, om, 1.f - kClamp * kClamp);
+        o.q = vfma(nh2, p.a2, omc);                                                  // NH^2 a2 + (1 - NH^2) (renderers.py:26)
+    } else {
+        o.q = 1.f - (o.NH * o.NH) * p.oma2;                       // NH^2 a2 + 1 - NH^2 (renderers.py:26)
+    }
     const T qc = vmax(o.q, kClamp);
     const T tV = vfma(o.VN2, p.oma2, p.a2);
     const T tL = vfma(o.LN2, p.oma2, p.a2);

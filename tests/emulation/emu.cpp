@@ -84,14 +84,14 @@ void loss_image_g(bool grey, const float* input, const float* target, int W, siz
     else      loss_image<T, false, MIXED, ENC>(input, target, W, HW, rec, N, lin, sr, sl, grad, a, b);
 }
 
-template <typename T>
+template <typename T, bool GREY>
 void render_image(const float* maps, int W, size_t HW, const float* rec, int N, const float* lin, float* images) {
     constexpr int L = LaneTraits<T>::kLanes;
     for (size_t p = 0; p < HW; p += L) {
         T v[12], x;
         for (int c = 0; c < 12; ++c) HostIO::ld(maps + c * HW + p, v[c]);
         HostIO::ld(lin + p % W, x);
-        render_pixel<T, HostIO>(v, x, -lin[p / W], rec, N, images + p, HW, true);
+        render_pixel<T, GREY, HostIO>(v, x, -lin[p / W], rec, N, images + p, HW, true);
     }
 }
 
@@ -159,8 +159,11 @@ void emu_render_forward(const float* maps, int B, int H, int W, const float* sce
     const bool packed = lanes == 2 || (lanes == 0 && (W & 1) == 0);
     for (int b = 0; b < B; ++b) {
         const float* rec = scenes + (per_batch ? (size_t)b * N * 9 : 0);
-        if (packed) render_image<F2>(maps + (size_t)b * 12 * HW, W, HW, rec, N, lin, images + (size_t)b * N * 3 * HW);
-        else        render_image<float>(maps + (size_t)b * 12 * HW, W, HW, rec, N, lin, images + (size_t)b * N * 3 * HW);
+        const float* m = maps + (size_t)b * 12 * HW;
+        float* im = images + (size_t)b * N * 3 * HW;
+        const bool grey = all_grey(per_batch ? scenes : rec, per_batch ? B * N : N);      // chosen per launch, like the library
+        if (packed) { if (grey) render_image<F2, true>(m, W, HW, rec, N, lin, im); else render_image<F2, false>(m, W, HW, rec, N, lin, im); }
+        else        { if (grey) render_image<float, true>(m, W, HW, rec, N, lin, im); else render_image<float, false>(m, W, HW, rec, N, lin, im); }
     }
 }
 

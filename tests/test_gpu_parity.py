@@ -46,6 +46,11 @@ def test_renders_vs_reference(S, golden, fixture):
     parity.check_tensor(got, g["renders_f32"], g["renders_f64"], "renders", rel=parity.REL_L2_STRESS if "stress" in fixture else parity.REL_L2)
     dlog = np.abs(np.log(got.astype(np.float64) + 0.1) - np.log(g["renders_f64"] + 0.1)).max()
     assert dlog < 2e-3, dlog
+    if fixture == "loss_bench":
+        # render_forward evaluates the GGX denominator in its accurate-highlight form (shading.cuh, ACC): on unit normals
+        # it is several times closer to the fp64 reference than the reference's own fp32 run, and within 1e-4 of that run
+        e64, floor = parity.rel_l2(got, g["renders_f64"]), parity.rel_l2(g["renders_f32"], g["renders_f64"])
+        assert e64 <= 0.25 * floor and e64 <= 2e-5, (e64, floor)
 
 
 def test_render_interface_fixed_scenes(S, golden):

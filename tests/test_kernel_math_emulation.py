@@ -30,6 +30,9 @@ def test_renders_three_way(golden, fixture, lanes):
     # the quantity the loss consumes
     dlog = np.abs(np.log(got.astype(np.float64) + 0.1) - np.log(g["renders_f64"] + 0.1)).max()
     assert dlog < 2e-3, dlog
+    if fixture == "loss_bench":      # accurate-highlight forward (shading.cuh, ACC): closer to fp64 than the reference's fp32 run
+        e64, floor = parity.rel_l2(got, g["renders_f64"]), parity.rel_l2(g["renders_f32"], g["renders_f64"])
+        assert e64 <= 0.25 * floor and e64 <= 2e-5, (e64, floor)
 
 
 def test_render_fixed_scenes(golden):
