@@ -76,3 +76,31 @@ def unambiguous_pixels(renders_in64, renders_tg64, thr=AMBIGUOUS_DLOG):
     l = np.abs(np.log(np.asarray(renders_in64, dtype=np.float64) + 0.1) - np.log(np.asarray(renders_tg64, dtype=np.float64) + 0.1))
     amb = ((l > 0) & (l < thr)).any(axis=(1, 2))
     return ~amb[:, None]
+
+
+def clamp_ambiguous_pixels(maps, cfg, rel=2e-3):
+    """[B,1,H,W] bool mask of the pixels where an argument of one of the reference's clamps (renderers.py:26,48-52,87,96)
+    sits within `rel` of its bound for some record / channel, evaluated in fp64: there the clamp's 0/1 gradient mask is a
+    coin flip for any fp32 evaluation (the reference's own included) and the gradient of the pixel is discontinuous."""
+    import torch
+    m = torch.as_tensor(maps).double()
+    c = torch.as_tensor(cfg).double()
+    B, _, H, W = m.shape
+    lin = torch.linspace(-1, 1, W, dtype=torch.float64)
+    px = torch.stack((lin.view(1, W).expand(H, W), -lin.view(H, 1).expand(H, W), torch.zeros(H, W, dtype=torch.float64)))   # [3,H,W]
+    n = m[:, None, 0:3]                                                                    # [B,1,3,H,W]
+    unit = lambda v: v / v.pow(2).sum(2, keepdim=True).sqrt()
+    wo = unit(c[:, :, 0:3, None, None] - px[None, None])                                   # [B,N,3,H,W]
+    wi = unit(c[:, :, 3:6, None, None] - px[None, None])
+    h = unit(wi + wo)
+    nh, vn, ln = (n * h).sum(2), (n * wo).sum(2), (n * wi).sum(2)                          # [B,N,H,W]
+    near = lambda x, b: (x - b).abs() <= rel * max(b, 1e-3)
+    amb = near(nh, 1e-3) | near(vn, 1e-3) | near(ln, 1e-3) | near(ln, 0.0)
+    nhc = nh.clamp(min=1e-3)
+    for ch in range(3):
+        rough = m[:, None, 6 + ch].clamp(min=1e-3)                                         # [B,1,H,W]
+        a2 = rough ** 4
+        q = nhc * nhc * (a2 + (1 - nhc * nhc) / (nhc * nhc))
+        amb = amb | near(q, 1e-3)
+    amb = amb.any(1) | near(m[:, 6:9], 1e-3).any(1)
+    return amb[:, None].numpy()

@@ -437,3 +437,14 @@ def test_full_resolution_gradient_parity(S, shape):
     g, g64 = x.grad.cpu().numpy(), g64.cpu().numpy()
     for name, s in parity.GROUPS:
         assert parity.rel_l2(g[:, s] * keep, g64[:, s] * keep) <= parity.REL_L2, name
+
+
+def test_random_shapes_against_the_oracle_on_gpu(S):
+    """scripts/fuzz_shapes.py through the CUDA library (see tests/test_kernel_math_emulation.py for the host twin)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_shapes.py"), "25", "11"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]

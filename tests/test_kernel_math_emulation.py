@@ -142,3 +142,16 @@ def test_degenerate_maps_stay_finite_and_match(golden):
         assert np.isfinite(loss) and np.isfinite(grad).all()
         assert abs(loss - float(l64)) <= 5e-6 * float(l64)
         assert parity.rel_l2(grad, g64.numpy()) <= 3e-4, parity.rel_l2(grad, g64.numpy())
+
+
+def test_random_shapes_against_the_oracle():
+    """scripts/fuzz_shapes.py on the host emulation: widths 1..70 (odd / even -> both lane types), 1..30 records, bench and
+    stress maps, grey and coloured lights; loss, gradient (over pixels without a sign- or clamp-ambiguous term, against the
+    reference's own fp32 noise), renders and render gradients vs the fp64 oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_shapes.py"), "12", "7", "--emu"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
