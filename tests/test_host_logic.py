@@ -231,3 +231,20 @@ def test_input_scene_sampler_and_noise_stream_match_reference(golden):
             outs.append(torch.clamp(images[k:k + 1] + noise, min=0.0, max=1.0))
         got = torch.cat(outs).numpy()
         np.testing.assert_allclose(got, g["inputs_" + tag], rtol=2e-4, atol=2e-5)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU port of the reference timed on the host cores) prints ONE JSON line with the
+    contract's keys; runs without a GPU."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "c1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "G evals/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "c1" and d["n_gpus"] == 1 and d["steps"] == 1
