@@ -59,8 +59,45 @@ for i in range(cases):
         rg = x2.grad.cpu().numpy()
     keep_r = ~parity.clamp_ambiguous_pixels(inp, cfg)
     e_rg = parity.rel_l2(rg * keep_r, m64.grad.numpy() * keep_r)
+    # MixedLoss (losses.py:54-63) on the maps and on the network's 9-channel encoding (models.py:334-346)
+    e_mix = e_enc = 0.0
+    if i % 2 == 0:
+        a64 = inp.double().requires_grad_(True)
+        m64l = O.mixed_loss(a64, tgt.double(), cfg, 0.1)
+        m64l.backward()
+        a32 = inp.clone().requires_grad_(True)
+        O.mixed_loss(a32, tgt, cfg, 0.1).backward()
+        if EMU:
+            (mtot, _, _), gm = emu.mixed_loss(inp.numpy(), tgt.numpy(), cfg.numpy(), 0.1)
+        else:
+            xm = inp.cuda().requires_grad_(True)
+            from svbrdf_estimation_b200.losses import _fused_loss
+            ml = _fused_loss(xm, tgt.cuda(), cfg, 0.1)
+            ml.backward()
+            mtot, gm = float(ml), xm.grad.cpu().numpy()
+        assert abs(mtot - float(m64l)) <= 5e-6 * abs(float(m64l)), ("mixed loss", W, B, mtot, float(m64l))
+        e_mix = parity.rel_l2(gm * keep, a64.grad.numpy() * keep)
+        assert e_mix <= max(3e-4, 2.0 * parity.rel_l2(a32.grad.numpy() * keep, a64.grad.numpy() * keep)), ("mixed gradient", W, B, e_mix)
+        enc = torch.rand(B, 9, W, W, generator=torch.Generator().manual_seed(300 + i)) * 2 - 1
+        e64 = enc.double().requires_grad_(True)
+        dec64 = O.decode_network_output(e64)
+        l64e = O.mixed_loss(dec64, tgt.double(), cfg, 0.1)
+        l64e.backward()
+        e32 = enc.clone().requires_grad_(True)
+        O.mixed_loss(O.decode_network_output(e32), tgt, cfg, 0.1).backward()
+        keep_e = parity.unambiguous_pixels(O.render_batch(dec64.detach(), cfg).numpy(), r64t) & ~parity.clamp_ambiguous_pixels(dec64.detach(), cfg)
+        if EMU:
+            (etot, _, _), ge = emu.mixed_loss(enc.numpy(), tgt.numpy(), cfg.numpy(), 0.1, encoded=True)
+        else:
+            xe = enc.cuda().requires_grad_(True)
+            le = S.mixed_loss_from_encoded(xe, tgt.cuda(), cfg, 0.1)[0]
+            le.backward()
+            etot, ge = float(le), xe.grad.cpu().numpy()
+        assert abs(etot - float(l64e)) <= 5e-6 * abs(float(l64e)), ("encoded mixed loss", W, B, etot, float(l64e))
+        e_enc = parity.rel_l2(ge * keep_e, e64.grad.numpy() * keep_e)
+        assert e_enc <= max(3e-4, 2.0 * parity.rel_l2(e32.grad.numpy() * keep_e, e64.grad.numpy() * keep_e)), ("encoded gradient", W, B, e_enc)
     tag = "W%-3d B%d N%-2d %s" % (W, B, nr + ns, "stress" if stress else "bench ")
-    print("%s loss %.1e grad %.1e render %.1e render-grad %.1e" % (tag, e_loss, e_grad, e_r, e_rg), flush=True)
+    print("%s loss %.1e grad %.1e render %.1e render-grad %.1e mixed-grad %.1e encoded-grad %.1e" % (tag, e_loss, e_grad, e_r, e_rg, e_mix, e_enc), flush=True)
     for k, v in (("loss", e_loss), ("grad", e_grad), ("render", e_r), ("rgrad", e_rg)):
         worst[k] = max(worst[k], v)
 print("worst:", worst)
