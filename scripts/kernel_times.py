@@ -36,6 +36,7 @@ def main():
     calls = {
         "loss_forward": (lambda: lib.svbrdf_b200_loss_forward(inp.data_ptr(), tgt.data_ptr(), B, size, size, rec.data_ptr(), N, lin.data_ptr(), out.data_ptr(), ws.data_ptr(), nb, st), 96 * P),
         "loss_forward_backward": (lambda: lib.svbrdf_b200_loss_forward_backward(inp.data_ptr(), tgt.data_ptr(), B, size, size, rec.data_ptr(), N, lin.data_ptr(), out.data_ptr(), grad.data_ptr(), ws.data_ptr(), nb, st), 144 * P),
+        "loss_forward_backward_accurate": (lambda: lib.svbrdf_b200_loss_forward_backward_accurate(inp.data_ptr(), tgt.data_ptr(), B, size, size, rec.data_ptr(), N, lin.data_ptr(), out.data_ptr(), grad.data_ptr(), ws.data_ptr(), nb, st), 144 * P),
         "mixed_loss_forward_backward": (lambda: lib.svbrdf_b200_mixed_loss_forward_backward(inp.data_ptr(), tgt.data_ptr(), B, size, size, rec.data_ptr(), N, 0.1, lin.data_ptr(), out.data_ptr(), grad.data_ptr(), ws.data_ptr(), nb, st), 144 * P),
         "mixed_loss_encoded_forward_backward": (lambda: lib.svbrdf_b200_mixed_loss_encoded_forward_backward(enc.data_ptr(), tgt.data_ptr(), B, size, size, rec.data_ptr(), N, 0.1, lin.data_ptr(), out.data_ptr(), genc.data_ptr(), ws.data_ptr(), nb, st), 120 * P),
         "render_forward": (lambda: lib.svbrdf_b200_render_forward(inp.data_ptr(), B, size, size, rec.data_ptr(), N, 1, lin.data_ptr(), images.data_ptr(), st), (48 + 12 * N) * P),

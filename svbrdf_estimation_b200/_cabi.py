@@ -36,6 +36,10 @@ PROTOTYPES = {
                                                          ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
                                                          _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
                                                          _c_stream]),
+    "svbrdf_b200_loss_forward_backward_accurate": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                                  ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
+                                                                  _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                                  _c_stream]),
     "svbrdf_b200_scale_grad": (ctypes.c_int, [_c_float_p, ctypes.c_size_t, _c_float_p, _c_stream]),
     "svbrdf_b200_mixed_loss_forward_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                                                ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float,

@@ -8,7 +8,8 @@ int svb_check_shape(int B, int H, int W, int N);
 
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded = false);
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded = false,
+                          bool accurate = false);
 int svb_ctas_per_image(int HW, int W);
 int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, int W, int N, bool mixed,
                         float l1_weight, float* out, int n_out, cudaStream_t st);

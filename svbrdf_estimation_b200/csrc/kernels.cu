@@ -148,7 +148,7 @@ __device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restric
 // ---------------------------------------------------------------------------------------------
 // ENC: `input` is the network's 9-channel encoded output [B,9,H,W] (decoded on the fly, gradient written
 // for the 9 encoded channels) instead of 12-channel maps.
-template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP>
+template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP, bool ACC = false>
 __global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
@@ -174,7 +174,7 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
-    const T lsum = loss_pixel<T, BWD, GREY>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    const T lsum = loss_pixel<T, BWD, GREY, ACC>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
     T l1 = LaneTraits<T>::splat(0.f);
     if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
     if (BWD && w.live) {
@@ -433,6 +433,13 @@ static bool all_grey(const float* recs, int nrec) {
     return true;
 }
 
+// accurate-highlight variant (svbrdf_b200_loss_forward_backward_accurate): RenderingLoss forward+backward only
+template <typename T, bool GREY>
+static cudaError_t launch_loss_acc(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, true, false, GREY, false, kCapSmall, true>, grid, a, recs, nrec, st)
+                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, false, GREY, false, kCapLarge, true>, grid, a, recs, nrec, st);
+}
+
 template <typename T, bool BWD, bool MIXED, bool GREY>
 static cudaError_t launch_loss_g(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
     return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapSmall>, grid, a, recs, nrec, st)
@@ -454,7 +461,9 @@ static cudaError_t launch_loss(bool small, dim3 grid, const LossArgs& a, const f
 }
 template <typename T>
 static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, const LossArgs& a, const float* recs,
-                                 int nrec, cudaStream_t st) {
+                                 int nrec, cudaStream_t st, bool accurate) {
+    if (accurate) return all_grey(recs, nrec) ? launch_loss_acc<T, true>(small, grid, a, recs, nrec, st)
+                                              : launch_loss_acc<T, false>(small, grid, a, recs, nrec, st);
     if (bwd) return mixed ? launch_loss<T, true, true>(small, grid, a, recs, nrec, st)
                           : launch_loss<T, true, false>(small, grid, a, recs, nrec, st);
     return mixed ? launch_loss<T, false, true>(small, grid, a, recs, nrec, st)
@@ -465,7 +474,7 @@ static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, co
 // the records do not fit one parameter block).  Pointers are for the WHOLE problem.
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded) {
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded, bool accurate) {
     const int cin = encoded ? 9 : 12;
     const int cpi = svb_ctas_per_image(HW, W);
     if (use_packed(W) && !(aligned(input, 8) && aligned(target, 8) && aligned(lin, 8) && (!grad || aligned(grad, 8))))
@@ -489,8 +498,8 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
         if (encoded)
             e = use_packed(W) ? launch_loss_enc<F2>(grid, a, recs, bc * N, st) : launch_loss_enc<float>(grid, a, recs, bc * N, st);
         else
-            e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st)
-                              : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st);
+            e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st, accurate)
+                              : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st, accurate);
         if (e != cudaSuccess) return cuda_status(e, "loss_kernel launch");
     }
     return 0;
@@ -516,7 +525,7 @@ int svb_launch_finalize(const float* part_render, const float* part_l1, int B, i
 
 static int loss_impl(const float* input, const float* target, int B, int H, int W, const float* scenes, int N,
                      const float* lin, float* out, int n_out, float* grad, void* ws, size_t ws_bytes,
-                     bool mixed, float l1_weight, void* stream, bool encoded = false) {
+                     bool mixed, float l1_weight, void* stream, bool encoded = false, bool accurate = false) {
     if (int e = svb_check_shape(B, H, W, N)) return e;
     if (!input || !target || !scenes || !lin || !out || !ws) return fail(SVBRDF_E_INVALID, "null pointer argument");
     if (ws_bytes < svbrdf_b200_workspace_bytes(B, N, H, W)) return fail(SVBRDF_E_INVALID, "workspace too small");
@@ -525,7 +534,7 @@ static int loss_impl(const float* input, const float* target, int B, int H, int 
     float* part_render = (float*)ws;
     float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, W);
     if (int e = svb_launch_loss_range(input, target, grad, B, HW, W, scenes, N, lin, part_render, part_l1, mixed,
-                                      l1_weight, 0, B, st, encoded))
+                                      l1_weight, 0, B, st, encoded, accurate))
         return e;
     return svb_launch_finalize(part_render, part_l1, B, HW, W, N, mixed, l1_weight, out, n_out, st);
 }
@@ -544,6 +553,15 @@ extern "C" int svbrdf_b200_loss_forward_backward(const float* input_dev, const f
     if (!grad_input_dev) return fail(SVBRDF_E_INVALID, "grad_input_dev is null");
     return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, grad_input_dev,
                      workspace_dev, workspace_bytes, false, 0.f, stream);
+}
+
+extern "C" int svbrdf_b200_loss_forward_backward_accurate(const float* input_dev, const float* target_dev, int B, int H, int W,
+                                                          const float* scenes_host, int N, const float* lin_dev,
+                                                          float* loss_dev, float* grad_input_dev, void* workspace_dev,
+                                                          size_t workspace_bytes, void* stream) {
+    if (!grad_input_dev) return fail(SVBRDF_E_INVALID, "grad_input_dev is null");
+    return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, grad_input_dev,
+                     workspace_dev, workspace_bytes, false, 0.f, stream, false, true);
 }
 
 extern "C" int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, const float* target_dev, int B, int H,

@@ -50,7 +50,8 @@ SVB_DEV bool all_or_none(B2 a, B2 b, B2 c) { return (a.x == b.x) && (b.x == c.x)
 // GREY: every record of the launch has r == g == b light colour (always true for the scenes
 // RenderingLoss samples, environment.py:27,52), so colour * falloff is formed once, not per channel.
 // Returns sum |log2 ratio| (ln2 and the mean are applied to the reduced loss).
-template <typename T, int NC, int C0, bool BWD, bool GREY>
+// ACC: accurate-highlight GGX denominator in both forward evaluations (shading.cuh shade_fwd<..., ACC>).
+template <typename T, int NC, int C0, bool BWD, bool GREY, bool ACC = false>
 SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y, const float* __restrict__ rec, int N,
                        Acc<T, NC>& acc) {
     T lsum = LaneTraits<T>::splat(0.f);
@@ -59,13 +60,13 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
         const float* __restrict__ rk = rec + k * kRecFloats;
         const Geo<T> g = make_geo<T>(x, y, rk);
         Fwd<T> fi, ft;
-#ifdef SVB_ACCURATE_LOSS       // build option: accurate-highlight forward in the loss kernels too (shading.cuh, ~ +13 % time)
-        shade_fwd<T, NC, BWD, true>(g, pi, fi);
-        shade_fwd<T, NC, false, true>(g, pt, ft);
+#ifdef SVB_ACCURATE_LOSS       // build option: accurate form in every loss kernel (~ +13 % time)
+        constexpr bool kAcc = true;
 #else
-        shade_fwd<T, NC, BWD>(g, pi, fi);
-        shade_fwd<T, NC, false>(g, pt, ft);
+        constexpr bool kAcc = ACC;
 #endif
+        shade_fwd<T, NC, BWD, kAcc>(g, pi, fi);
+        shade_fwd<T, NC, false, kAcc>(g, pt, ft);
         // radiance + 0.1 of both maps (losses.py:46-47); E = light colour * falloff / pi
         T E[NC], fin[NC], xi[NC], xt[NC];
         if (GREY) {
@@ -128,14 +129,14 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
 
 // One single-channel pass (general path): channel C of input/target with its own roughness.  `live`
 // masks lanes whose channel-C inputs are bitwise identical (their exact contribution is 0).
-template <typename T, int C, bool BWD, bool GREY>
+template <typename T, int C, bool BWD, bool GREY, bool ACC = false>
 SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
                             float nscale, typename LaneTraits<T>::Mask live, T (&g)[12]) {
     const Pix<T, 1> pi = make_pix<T, 1>(&vi[0], &vi[3 + C], &vi[9 + C], vi[6 + C]);
     const Pix<T, 1> pt = make_pix<T, 1>(&vt[0], &vt[3 + C], &vt[9 + C], vt[6 + C]);
     Acc<T, 1> acc;
     acc_zero(acc);
-    const T l = loss_records<T, 1, C, BWD, GREY>(pi, pt, x, y, rec, N, acc);
+    const T l = loss_records<T, 1, C, BWD, GREY, ACC>(pi, pt, x, y, rec, N, acc);
     if (BWD) {
         const T ns = vsel(live, LaneTraits<T>::splat(nscale), 0.f);    // masked lanes: scale 0
         T gd[1], gs[1];
@@ -157,7 +158,7 @@ SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, 
 // case is handled explicitly: the fast path requires that, per pixel, either all three channels differ
 // or none does (fully identical pixels are zeroed at the end); anything else takes the channel-wise path
 // where identical channels are masked.
-template <typename T, bool BWD, bool GREY>
+template <typename T, bool BWD, bool GREY, bool ACC = false>
 SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
                      float scale, T (&g)[12]) {
     typedef typename LaneTraits<T>::Mask M;
@@ -169,7 +170,7 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
         const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
         Acc<T, 3> acc;
         acc_zero(acc);
-        const T l = loss_records<T, 3, 0, BWD, GREY>(pi, pt, x, y, rec, N, acc);
+        const T l = loss_records<T, 3, 0, BWD, GREY, ACC>(pi, pt, x, y, rec, N, acc);
         if (BWD) {
             const T ns = vsel(d0, LaneTraits<T>::splat(nscale), 0.f);  // fully identical pixels: scale 0
             const T chain = rough_chain(vi[6]) * ns;
@@ -187,9 +188,9 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
     }
     // general path: three single-channel passes (the loss and all gradients decompose by colour channel)
     if (BWD) { g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f); }
-    T l = loss_channel_pass<T, 0, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d0, g);
-    l = l + loss_channel_pass<T, 1, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d1, g);
-    l = l + loss_channel_pass<T, 2, BWD, GREY>(vi, vt, x, y, rec, N, nscale, d2, g);
+    T l = loss_channel_pass<T, 0, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d0, g);
+    l = l + loss_channel_pass<T, 1, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d1, g);
+    l = l + loss_channel_pass<T, 2, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d2, g);
     return l;
 }
 

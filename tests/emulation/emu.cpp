@@ -49,7 +49,7 @@ bool all_grey(const float* recs, int nrec) {
 
 // One image: rendering-loss (+ map-L1 when MIXED) forward+backward.  ENC: `input` is the 9-channel network
 // output, grad has 9 channels.  Returns the unscaled sums (log2 units for the rendering part).
-template <typename T, bool GREY, bool MIXED, bool ENC>
+template <typename T, bool GREY, bool MIXED, bool ENC, bool ACC = false>
 void loss_image(const float* input, const float* target, int W, size_t HW, const float* rec, int N, const float* lin,
                 float scale_render, float scale_l1, float* grad, double* sum_render, double* sum_l1) {
     constexpr int L = LaneTraits<T>::kLanes;
@@ -64,7 +64,7 @@ void loss_image(const float* input, const float* target, int W, size_t HW, const
         }
         for (int c = 0; c < 12; ++c) HostIO::ld(target + c * HW + p, vt[c]);
         HostIO::ld(lin + p % W, x);
-        const T l = loss_pixel<T, true, GREY>(vi, vt, x, -lin[p / W], rec, N, scale_render, g);
+        const T l = loss_pixel<T, true, GREY, ACC>(vi, vt, x, -lin[p / W], rec, N, scale_render, g);
         *sum_render += (double)hsum(l);
         if (MIXED) *sum_l1 += (double)hsum(l1_pixel<T, true>(vi, vt, scale_l1, g));
         if (ENC) {
@@ -142,6 +142,26 @@ void emu_loss(const float* input, const float* target, int B, int H, int W, cons
     out[1] = a * (double)kLn2 / ((double)B * N * 3.0 * (double)HW);
     out[2] = b / ((double)B * 3.0 * (double)HW);
     out[0] = out[1] + ((mixed || encoded) ? (double)l1_weight * out[2] : 0.0);
+}
+
+// RenderingLoss forward+backward with the accurate-highlight forward (svbrdf_b200_loss_forward_backward_accurate).
+double emu_loss_forward_backward_accurate(const float* input, const float* target, int B, int H, int W, const float* scenes,
+                                          int N, const float* lin, float* grad, int lanes) {
+    const size_t HW = (size_t)H * W;
+    const bool packed = lanes == 2 || (lanes == 0 && (W & 1) == 0);
+    const bool grey = all_grey(scenes, B * N);
+    const float sr = (float)(1.0 / ((double)B * N * 3.0 * (double)HW));
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < B; ++i) {
+        const float* rec = scenes + (size_t)i * N * 9;
+        const float *pi = input + (size_t)i * 12 * HW, *pt = target + (size_t)i * 12 * HW;
+        float* pg = grad + (size_t)i * 12 * HW;
+        if (packed) { if (grey) loss_image<F2, true, false, false, true>(pi, pt, W, HW, rec, N, lin, sr, 0.f, pg, &a, &b);
+                      else      loss_image<F2, false, false, false, true>(pi, pt, W, HW, rec, N, lin, sr, 0.f, pg, &a, &b); }
+        else        { if (grey) loss_image<float, true, false, false, true>(pi, pt, W, HW, rec, N, lin, sr, 0.f, pg, &a, &b);
+                      else      loss_image<float, false, false, false, true>(pi, pt, W, HW, rec, N, lin, sr, 0.f, pg, &a, &b); }
+    }
+    return a * (double)kLn2 / ((double)B * N * 3.0 * (double)HW);
 }
 
 // RenderingLoss only (the original entry point of this file).

@@ -20,6 +20,7 @@ def lib():
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", LIB, SRC])
         _lib = ctypes.CDLL(LIB)
         _lib.emu_loss_forward_backward.restype = ctypes.c_double
+        _lib.emu_loss_forward_backward_accurate.restype = ctypes.c_double
     return _lib
 
 
@@ -36,12 +37,13 @@ def lin_table(w):
     return torch.linspace(-1, 1, w, dtype=torch.float32).numpy()
 
 
-def loss_forward_backward(inp, tgt, scenes, lanes=0):
+def loss_forward_backward(inp, tgt, scenes, lanes=0, accurate=False):
     inp, tgt, scenes = _f32(inp), _f32(tgt), _f32(scenes)
     B, _, H, W = inp.shape
     grad = np.empty_like(inp)
     lin = lin_table(W)
-    loss = lib().emu_loss_forward_backward(_p(inp), _p(tgt), B, H, W, _p(scenes), scenes.shape[1], _p(lin), _p(grad), lanes)
+    fn = lib().emu_loss_forward_backward_accurate if accurate else lib().emu_loss_forward_backward
+    loss = fn(_p(inp), _p(tgt), B, H, W, _p(scenes), scenes.shape[1], _p(lin), _p(grad), lanes)
     return loss, grad
 
 

@@ -448,3 +448,27 @@ def test_random_shapes_against_the_oracle_on_gpu(S):
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_shapes.py"), "25", "11"],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
+
+
+def test_accurate_rendering_loss(S, golden):
+    """RenderingLoss(..., accurate=True) / rendering_loss_with_records(..., accurate=True): the accurate-highlight kernels.
+    Golden fixture: gradients several times closer to fp64 than the reference's own fp32 run; full resolution: 1e-5."""
+    g = golden("loss_bench")
+    x = cu(g["input"]).requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, cu(g["target"]), torch.from_numpy(g["configs"]), accurate=True)
+    loss.backward()
+    parity.check_loss(float(loss), g["loss_f64"])
+    grad = x.grad.cpu().numpy()
+    for name, s in parity.GROUPS:
+        e64 = parity.rel_l2(grad[:, s], g["grad_f64"][:, s])
+        floor = parity.rel_l2(g["grad_f32"][:, s], g["grad_f64"][:, s])
+        assert e64 <= max(0.3 * floor, 3e-7), (name, e64, floor)
+    # module form, no-grad form, and agreement with the default kernels to the default kernels' accuracy
+    mod = S.RenderingLoss(S.LocalRenderer(), accurate=True)
+    torch.manual_seed(3)
+    a = float(mod(cu(g["input"]), cu(g["target"])))
+    torch.manual_seed(3)
+    b = float(S.RenderingLoss(S.LocalRenderer())(cu(g["input"]), cu(g["target"])))
+    assert abs(a - b) <= 2e-6 * abs(b)
+    with pytest.raises(NotImplementedError):
+        S.losses._fused_loss(x, cu(g["target"]), torch.from_numpy(g["configs"]), 0.1, True)

@@ -155,3 +155,16 @@ def test_random_shapes_against_the_oracle():
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_shapes.py"), "12", "7", "--emu"],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_accurate_loss_is_closer_to_fp64_than_the_reference_fp32_run(golden, lanes):
+    """svbrdf_b200_loss_forward_backward_accurate (host twin): on unit-normal inputs every gradient group is several times
+    closer to the fp64 reference than the reference's own fp32 run."""
+    g = golden("loss_bench")
+    loss, grad = emu.loss_forward_backward(g["input"], g["target"], g["configs"], lanes, accurate=True)
+    parity.check_loss(loss, g["loss_f64"])
+    for name, s in parity.GROUPS:
+        e64 = parity.rel_l2(grad[:, s], g["grad_f64"][:, s])
+        floor = parity.rel_l2(g["grad_f32"][:, s], g["grad_f64"][:, s])
+        assert e64 <= max(0.3 * floor, 3e-7), (name, e64, floor)
