@@ -401,6 +401,18 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        # informational: the same call when the gradient is left on the device (what a training loop does with it)
+        def e2e_step_nograd(i):
+            rec = records[i % len(records)]
+            _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], B, rec.data_ptr(), N, ctypes.byref(lossf), None))
+        for i in range(2):
+            e2e_step_nograd(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step_nograd(i)
+        torch.cuda.synchronize()
+        dt_ng = time.perf_counter() - t0
         # parity of the two entry points on the same inputs (bitwise: same kernels, same coordinates)
         step(0)
         torch.cuda.synchronize()
@@ -412,7 +424,10 @@ def run_ours(args):
         e2e = {"value": world * evals_per_step / (dt / e2e_steps) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": 2 * nfl * 4, "d2h_bytes_per_step": nfl * 4 + 4, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3, "entry": "svbrdf_b200_rendering_loss_host (pinned host maps -> loss + grad on host)",
-               "matches_device_entry": bool(same), "host_placement": numa_note}
+               "matches_device_entry": bool(same), "host_placement": numa_note,
+               "loss_only_variant": {"value": evals_per_step / (dt_ng / e2e_steps) / 1e9, "unit": UNIT, "ms_per_step": dt_ng / e2e_steps * 1e3,
+                                     "d2h_bytes_per_step": 4, "note": "per rank; forward only (no gradient is computed or downloaded): "
+                                     "the upload alone, i.e. the PCIe floor of this entry point"}}
 
     if rank != 0:
         if world > 1:
