@@ -218,7 +218,7 @@ def run_reference(args):
             "note": "reference = its eager-PyTorch CPU path restated in oracle/reference_port.py (bit-exact to the "
                     "reference in fp32, tests/test_oracle_golden.py); the reference itself is Python source that does "
                     "not exist on the GPU box"}
-    print(json.dumps(line))
+    args.out.emit(json.dumps(line))
     return 0
 
 
@@ -261,8 +261,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()
     B, size, N, nr, ns, desc = WORKLOADS[args.workload]
@@ -499,10 +497,24 @@ def run_ours(args):
             "gpu_launches_note": "per step: 1 fused loss fwd+bwd kernel + 1 single-CTA finalize kernel",
             "clocks": sampler.summary(clock_note),
             "step_ms_with_event_per_step": {"min": per_step[0], "median": statistics.median(per_step), "max": per_step[-1], "n": len(per_step)}}
-    print(json.dumps(line))
+    args.out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+class OnlyJsonOnStdout:
+    """Everything any library writes to file descriptor 1 during the run (NCCL prints its version banner there) goes to
+    stderr; `emit` writes the one JSON line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
 
 
 def main():
@@ -515,6 +527,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.out = OnlyJsonOnStdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
