@@ -226,8 +226,15 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 def probe_fp32_peaks(lib, torch, stream):
-    """Measured register-resident FP32 rates in TFLOP/s (FMA = 2): scalar FFMA, packed FFMA2, FMUL+FADD mix."""
-    from svbrdf_estimation_b200 import _cabi
+    """Measured register-resident FP32 rates in TFLOP/s (FMA = 2): scalar FFMA, packed FFMA2, FMUL+FADD mix.
+    The probe kernels live in a bench-only object (scripts/fp32_probe.cu -> scripts/libfp32_probe.so), not in the
+    product library."""
+    path = os.path.join(ROOT, "scripts", "libfp32_probe.so")
+    if not os.path.exists(path):
+        return {}
+    probe = ctypes.CDLL(path)
+    probe.fp32_probe_launch.restype = ctypes.c_int
+    probe.fp32_probe_launch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     blocks, iters = sms * 16, 4000
     sink = torch.zeros(blocks * 256, device="cuda")
@@ -237,7 +244,9 @@ def probe_fp32_peaks(lib, torch, stream):
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _cabi.check(lib.svbrdf_b200_probe_launch(kind, blocks, iters, sink.data_ptr(), ctypes.byref(ops), stream))
+            rc = probe.fp32_probe_launch(kind, blocks, iters, sink.data_ptr(), ctypes.byref(ops), stream)
+            if rc != 0:
+                return out
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)

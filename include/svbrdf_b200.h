@@ -15,7 +15,9 @@
  *
  * Conventions
  *   - Plain pointers and sizes only.  All "dev" pointers are device memory of the CURRENT
- *     CUDA device, fp32, contiguous NCHW; "host" pointers are ordinary host memory.
+ *     CUDA device, fp32, contiguous NCHW, 4-byte aligned (8-byte aligned pointers and an even W
+ *     select the two-pixels-per-thread kernels; anything else runs the one-pixel-per-thread ones);
+ *     "host" pointers are ordinary host memory.
  *   - The caller owns every buffer.  The library allocates nothing in the device-pointer
  *     entry points, keeps no state between calls, and is re-entrant.  (The *_host entry
  *     points use an explicit context object that owns staging buffers and streams.)
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SVBRDF_B200_ABI_VERSION 1
+#define SVBRDF_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SVBRDF_API __attribute__((visibility("default")))
@@ -57,6 +59,10 @@ SVBRDF_API int svbrdf_b200_abi_version(void);
 
 /* Thread-local description of the last non-zero status returned on this thread. */
 SVBRDF_API const char* svbrdf_b200_last_error(void);
+
+/* Hash of the CUDA sources this binary was built from (svbrdf_estimation_b200/_build.py); the Python binding
+ * compares it with the sources on disk and refuses (or rebuilds) a stale library.                       */
+SVBRDF_API const char* svbrdf_b200_build_id(void);
 
 /* Bytes of device workspace the loss entry points need for a [B,12,H,W] problem with N
  * scene records per batch element (per-CTA loss partials).  Never 0.                      */
@@ -76,6 +82,35 @@ SVBRDF_API int svbrdf_b200_coordinate_table(float* lin_host, int W);
  * samplers in environment.py reproduce the reference's torch draws).  Host-only, no CUDA call.       */
 SVBRDF_API int svbrdf_b200_sample_scenes(uint64_t seed, int first_batch_element, int B, int n_random,
                                          int n_specular, float* records_host);
+
+/* The random draws of RenderingLoss.forward's samplers for B batch elements (losses.py:35: generate_random_scenes(
+ * n_random) + generate_specular_scenes(n_specular) per element; environment.py:18-55, utils.py:100-111), taken from
+ * torch's global CPU generator in the reference's order.  torch_cpu_rng_state is the buffer of torch.get_rng_state()
+ * (5056 bytes: at::CPUGeneratorImplState); it is advanced in place - hand it to torch.set_rng_state() afterwards and
+ * torch continues exactly where the reference's own calls would have left it.
+ *   uniforms_host [B][4*n_random + 4*n_specular]: raw uniform_(0,1) draws per element in stream order
+ *                 (view r1.., r2.., light r1.., r2.. | specular view r1.., r2.. | shift x0,y0,x1,y1..)
+ *   normals_host  [B][2][n_specular]: the normal_(0.5, 0.75) log-distances (view, light)
+ * n_specular must be < 16 (normal_() on larger tensors takes ATen's vectorised path).  Host-only, no CUDA call.  */
+SVBRDF_API int svbrdf_b200_reference_draws(void* torch_cpu_rng_state, size_t state_bytes, int B, int n_random,
+                                int n_specular, float* uniforms_host, float* normals_host);
+
+/* The same sampling in the two-phase form RenderingLoss uses: everything of environment.py:18-55 / utils.py:100-111
+ * except sqrt, cos, sin and exp (torch's vectorised / MKL implementations, applied by the caller to whole-batch
+ * tensors between the two calls) - draws, uniform_(lo, hi) maps, products and sums, each rounded to float where the
+ * reference's float32 tensor ops round.  Directions per batch element: n_random views, n_random lights, n_specular
+ * mirror views.
+ *   begin : r1_host, phi_host [B][2*n_random + n_specular]; log_distance_host [B][2][n_specular];
+ *           shift_host [B][n_specular][2]; advances torch_cpu_rng_state like svbrdf_b200_reference_draws
+ *   finish: radius_host = torch.sqrt(r1), cos_phi_host / sin_phi_host = torch.cos / torch.sin(phi),
+ *           z_host = torch.sqrt(1 - radius * radius), distance_host = torch.exp(log_distance)
+ *           ->  records_host [B][n_random + n_specular][9], bit-identical to the reference's scenes            */
+SVBRDF_API int svbrdf_b200_reference_scenes_begin(void* torch_cpu_rng_state, size_t state_bytes, int B, int n_random,
+                                int n_specular, float* r1_host, float* phi_host,
+                                float* log_distance_host, float* shift_host);
+SVBRDF_API int svbrdf_b200_reference_scenes_finish(int B, int n_random, int n_specular, const float* radius_host,
+                                const float* cos_phi_host, const float* sin_phi_host, const float* z_host,
+                                const float* distance_host, const float* shift_host, float* records_host);
 
 /* ---- LocalRenderer.render (renderers.py:67-104) ------------------------------------------
  * images[b,k,:,:,:] = radiance of maps[b] under scene record k of batch element b.
@@ -117,6 +152,12 @@ SVBRDF_API int svbrdf_b200_loss_forward_backward_accurate(const float* input_dev
                                       int B, int H, int W, const float* scenes_host, int N,
                                       const float* lin_dev, float* loss_dev, float* grad_input_dev,
                                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Forward-only form of the accurate-highlight evaluation (no gradient buffer).                              */
+SVBRDF_API int svbrdf_b200_loss_forward_accurate(const float* input_dev, const float* target_dev, int B, int H, int W,
+                             const float* scenes_host, int N, const float* lin_dev,
+                             float* loss_dev, void* workspace_dev, size_t workspace_bytes,
+                             void* stream);
 
 /* grad[i] *= *upstream_dev for i < count, in place; returns immediately on the device when
  * *upstream_dev == 1.0f (the loss.backward() case), so no host synchronisation is needed
@@ -162,14 +203,6 @@ SVBRDF_API float* svbrdf_b200_ctx_pinned(svbrdf_b200_ctx* ctx, int which);
 SVBRDF_API int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* ctx, const float* input_host,
                                     const float* target_host, int B, const float* scenes_host,
                                     int N, float* loss_host, float* grad_host);
-
-/* ---- measurement helpers (bench.py only) -------------------------------------------------------
- * Register-resident FP32 throughput probes used as measured roofline denominators.
- * kind: 0 = independent scalar FFMA chains, 1 = packed fma.rn.f32x2 (FFMA2), 3 = FMUL+FADD mix (1 FLOP each).
- * Launches `blocks` CTAs of 256 threads running `iters` unrolled groups; *ops_per_thread_iter
- * receives the number of counted operations (FMA = 1 op) per thread per iteration.          */
-SVBRDF_API int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* sink_dev,
-                             int* ops_per_thread_iter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,23 +18,25 @@ VDIR = os.path.join(ROOT, "variants")
 
 
 def build(specs):
+    from concurrent.futures import ThreadPoolExecutor
     from svbrdf_estimation_b200 import _build
     os.makedirs(VDIR, exist_ok=True)
     for f in glob.glob(os.path.join(VDIR, "*.so")):
         os.remove(f)
-    procs = []
-    for spec in specs:
+
+    def one(spec):
         name, _, flags = spec.partition("=")
-        out = os.path.join(VDIR, name + ".so")
-        cmd = [_build.find_nvcc()] + _build.NVCC_FLAGS + flags.split() + ["-shared", "-o", out] + \
-              [os.path.join(_build.CSRC, s) for s in _build.SOURCES]
-        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for name, p in procs:
-        out, _ = p.communicate()
-        print(name, "OK" if p.returncode == 0 else "FAILED\n" + out)
+        try:
+            _build.compile_library(os.path.join(VDIR, name + ".so"), extra_flags=flags.split())
+            return name, "OK"
+        except Exception as exc:
+            return name, "FAILED %s" % exc
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        for name, status in pool.map(one, specs):
+            print(name, status)
 
 
-def run(workload="c2", steps=100):
+def run(workload="c2", steps=100, entry="svbrdf_b200_loss_forward_backward"):
     import torch
     import bench
     from svbrdf_estimation_b200 import _cabi
@@ -61,8 +63,8 @@ def run(workload="c2", steps=100):
 
         def step(i):
             a, b, g = sets[i % 2]
-            rc = lib.svbrdf_b200_loss_forward_backward(a.data_ptr(), b.data_ptr(), B, size, size, rec.data_ptr(), N,
-                                                       lin.data_ptr(), loss.data_ptr(), g.data_ptr(), ws.data_ptr(), wsb, st)
+            rc = getattr(lib, entry)(a.data_ptr(), b.data_ptr(), B, size, size, rec.data_ptr(), N,
+                                     lin.data_ptr(), loss.data_ptr(), g.data_ptr(), ws.data_ptr(), wsb, st)
             assert rc == 0, lib.svbrdf_b200_last_error()
         for i in range(5):
             step(i)
@@ -74,7 +76,7 @@ def run(workload="c2", steps=100):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        rows.append({"variant": os.path.basename(path)[:-3], "ms": ms, "G_evals_s": evals / ms / 1e6,
+        rows.append({"variant": os.path.basename(path)[:-3], "workload": workload, "entry": entry.replace("svbrdf_b200_", ""), "ms": ms, "G_evals_s": evals / ms / 1e6,
                      "loss": float(loss.item()), "gsum": float(sets[(steps - 1) % 2][2].double().abs().sum().item())})
         print(json.dumps(rows[-1]))
     return rows
@@ -84,4 +86,7 @@ if __name__ == "__main__":
     if sys.argv[1] == "build":
         build(sys.argv[2:])
     else:
-        run(*(sys.argv[2:3]))
+        for w in (sys.argv[2:] or ["c2"]):
+            run(w)
+            if w == "c2":
+                run(w, entry="svbrdf_b200_loss_forward_backward_accurate")

@@ -193,7 +193,8 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
     int rc = 0, prev = -1;
     cudaGetDevice(&prev);
     const int HW = c->H * c->W;
-    const int cpi = svb_ctas_per_image(HW, c->W);
+    const bool packed = (c->W & 1) == 0;          // cudaMalloc'd buffers: aligned
+    const int cpi = svb_ctas_per_image(HW, packed);
     float* part_render = c->d_ws;
     float* part_l1 = c->d_ws + (size_t)B * cpi;
     // slices: enough to overlap the two copy directions with compute, not so many that launch
@@ -211,7 +212,7 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
             CK(cudaStreamWaitEvent(c->s_comp, c->ev_up[i], 0));
             CK(cudaStreamWaitEvent(c->s_comp, c->ev_up2[i], 0));
             rc = svb_launch_loss_range(c->d_in, c->d_tg, grad_host ? c->d_gr : nullptr, B, HW, c->W, scenes_host, N,
-                                       c->d_lin, part_render, part_l1, false, 0.f, b0, b1 - b0, c->s_comp);
+                                       c->d_lin, part_render, part_l1, false, 0.f, b0, b1 - b0, c->s_comp, packed);
             if (rc) goto done;
             if (grad_host) {
                 CK(cudaEventRecord(c->ev_k[i], c->s_comp));
@@ -219,7 +220,7 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
                 CK(cudaMemcpyAsync(grad_host + off, c->d_gr + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        rc = svb_launch_finalize(part_render, part_l1, B, HW, c->W, N, false, 0.f, c->d_loss, 1, c->s_comp);
+        rc = svb_launch_finalize(part_render, part_l1, B, HW, packed, N, false, 0.f, c->d_loss, 1, c->s_comp);
         if (rc) goto done;
         CK(cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
         CK(cudaStreamSynchronize(c->s_comp));

@@ -6,10 +6,12 @@ int svb_fail(int code, const char* msg);
 int svb_cuda_status(cudaError_t e, const char* where);
 int svb_check_shape(int B, int H, int W, int N);
 
+// packed = two pixels per thread (W even, 8-byte aligned pointers); decides the CTA count per image
+bool svb_loss_packed(int W, const void* input, const void* target, const void* grad, const void* lin);
+int svb_ctas_per_image(int HW, bool packed);
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded = false,
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool packed, bool encoded = false,
                           bool accurate = false);
-int svb_ctas_per_image(int HW, int W);
-int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, int W, int N, bool mixed,
+int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, bool packed, int N, bool mixed,
                         float l1_weight, float* out, int n_out, cudaStream_t st);

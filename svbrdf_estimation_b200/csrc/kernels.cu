@@ -148,8 +148,33 @@ __device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restric
 // ---------------------------------------------------------------------------------------------
 // ENC: `input` is the network's 9-channel encoded output [B,9,H,W] (decoded on the fly, gradient written
 // for the 9 encoded channels) instead of 12-channel maps.
-template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP, bool ACC = false>
-__global__ void __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
+//
+// ROWTAB (packed lanes, W % 64 == 0, N <= kRowTabMaxN): the 64 pixels of a warp lie in one image row, so everything
+// a scene record contributes that does not depend on the column - light/camera y and z offsets, their squared sums,
+// colour / pi (shading.cuh RecScalars) - is formed ONCE per warp into a shared-memory table (lane k fills record k)
+// and read back in the record loop with three broadcast LDS.128, instead of 7 indexed constant loads and 7 scalar
+// FP operations per thread and record.  Same operations on the same values: bit-identical to the other path.
+constexpr int kRowTabMaxN = 64;
+struct RowTabRecs {
+    const float4* tab;     // [N][3]
+    __device__ __forceinline__ RecScalars get(int k) const {
+        const float4 a = tab[3 * k], b = tab[3 * k + 1], c = tab[3 * k + 2];
+        RecScalars r;
+        r.sx = a.x; r.vx = a.y; r.ly = a.z; r.lz = a.w;
+        r.lyz = b.x; r.vy = b.y; r.vz = b.z; r.vyz = b.w;
+        r.col[0] = c.x; r.col[1] = c.y; r.col[2] = c.z;
+        return r;
+    }
+};
+extern __shared__ float4 svb_rowtab[];
+
+#ifdef SVB_LOSS_MAXNREG         // A/B builds: an explicit register cap instead of the one implied by kMinBlocks
+#define SVB_LOSS_BOUNDS __maxnreg__(SVB_LOSS_MAXNREG)
+#else
+#define SVB_LOSS_BOUNDS __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
+#endif
+template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP, bool ACC = false, bool ROWTAB = false>
+__global__ void SVB_LOSS_BOUNDS
 loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
     constexpr int CIN = ENC ? 9 : 12;
@@ -174,7 +199,21 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     load12<T>(a.target + off, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
-    const T lsum = loss_pixel<T, BWD, GREY, ACC>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    T lsum;
+    if (ROWTAB) {
+        float4* tab = svb_rowtab + (threadIdx.x >> 5) * (3 * a.N);
+        for (int k = threadIdx.x & 31; k < a.N; k += 32) {
+            const RecScalars r = rec_scalars(rec + k * kRecFloats, w.y);
+            tab[3 * k] = make_float4(r.sx, r.vx, r.ly, r.lz);
+            tab[3 * k + 1] = make_float4(r.lyz, r.vy, r.vz, r.vyz);
+            tab[3 * k + 2] = make_float4(r.col[0], r.col[1], r.col[2], 0.f);
+        }
+        __syncwarp();
+        const RowTabRecs recs{tab};
+        lsum = loss_pixel_rs<T, BWD, GREY, ACC, RowTabRecs>(vi, vt, w.x, recs, a.N, a.scale_render, g);
+    } else {
+        lsum = loss_pixel<T, BWD, GREY, ACC>(vi, vt, w.x, w.y, rec, a.N, a.scale_render, g);
+    }
     T l1 = LaneTraits<T>::splat(0.f);
     if (MIXED) l1 = l1_pixel<T, BWD>(vi, vt, a.scale_l1, g);
     if (BWD && w.live) {
@@ -321,40 +360,6 @@ scale_kernel(float* __restrict__ g, size_t count, const float* __restrict__ upst
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) g[i] *= u;
 }
 
-// ---------------------------------------------------------------------------------------------
-// FP32 throughput probes (bench.py: measured denominators for the FP32 roofline)
-// ---------------------------------------------------------------------------------------------
-template <int KIND>
-__global__ void __launch_bounds__(256)
-probe_kernel(int iters, float* __restrict__ sink) {
-    float r[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = 1.0f + 1e-3f * (float)((threadIdx.x + i) & 7);
-    const float m = 0.9999f + 1e-7f * (float)(threadIdx.x & 3), c = 1e-4f;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (KIND == 0) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], m, c);
-            } else if (KIND == 1) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const F2 t = vfma(mk2(r[i], r[i + 1]), mk2(m, m), mk2(c, c));
-                    r[i] = lo(t); r[i + 1] = hi(t);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) { r[i] = r[i] * m; r[i + 1] = r[i + 1] + c; }
-            }
-        }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s += r[i];
-    if (s == 123.456f) sink[blockIdx.x * 256 + threadIdx.x] = s;   // keeps the chain alive
-}
-
 }  // namespace svb
 
 // =============================================================================================
@@ -385,19 +390,29 @@ int svb_check_shape(int B, int H, int W, int N) {
 }
 
 // Packed (two pixels per thread) kernels need pixel pairs that never straddle a row and 8-byte
-// aligned planes: W even (H == W, so H*W is even too).
-static inline bool use_packed(int W) { return (W & 1) == 0; }
-static inline int pixels_per_cta(int W) { return use_packed(W) ? 2 * Cfg<F2>::kThreads : Cfg<float>::kThreads; }
-int svb_ctas_per_image(int HW, int W) { return (HW + pixels_per_cta(W) - 1) / pixels_per_cta(W); }
+// aligned planes: W even (H == W, so H*W is even too) and 8-byte aligned base pointers.  Anything else - odd widths,
+// or a contiguous view that starts at an odd float offset - takes the one-pixel-per-thread kernels, which only need
+// the natural 4-byte alignment of a float.
+static inline bool aligned8(const void* p) { return ((uintptr_t)p & 7u) == 0; }
+static inline int pixels_per_cta(bool packed) { return packed ? 2 * Cfg<F2>::kThreads : Cfg<float>::kThreads; }
+int svb_ctas_per_image(int HW, bool packed) { return (HW + pixels_per_cta(packed) - 1) / pixels_per_cta(packed); }
+bool svb_loss_packed(int W, const void* input, const void* target, const void* grad, const void* lin) {
+    return (W & 1) == 0 && aligned8(input) && aligned8(target) && aligned8(lin) && (!grad || aligned8(grad));
+}
 
 extern "C" int svbrdf_b200_abi_version(void) { return SVBRDF_B200_ABI_VERSION; }
 extern "C" const char* svbrdf_b200_last_error(void) { return g_err; }
+#ifndef SVB_BUILD_ID
+#define SVB_BUILD_ID "unknown"
+#endif
+extern "C" const char* svbrdf_b200_build_id(void) { return SVB_BUILD_ID; }
 
 extern "C" size_t svbrdf_b200_workspace_bytes(int B, int N, int H, int W) {
     (void)N;
     if (B <= 0 || H <= 0 || W <= 0) return 256;
-    const size_t ctas = (size_t)B * (size_t)svb_ctas_per_image(H * W, W);
-    return 2 * ctas * sizeof(float) + 256;     // render partials + map-L1 partials
+    const int a = svb_ctas_per_image(H * W, true), b = svb_ctas_per_image(H * W, false);
+    const size_t ctas = (size_t)B * (size_t)(a > b ? a : b);     // whichever kernel family the pointers will select
+    return 2 * ctas * sizeof(float) + 256;                       // render partials + map-L1 partials
 }
 
 // Batch elements per launch such that the launch's records fit the parameter block.
@@ -417,10 +432,10 @@ static inline int balanced_chunk(int total, int cap) {
 
 template <int CAP, int THREADS, typename Args, typename Kernel>
 static cudaError_t launch_with_scenes(Kernel kernel, dim3 grid, const Args& args, const float* recs, int nrec,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, size_t smem = 0) {
     SceneBlock<CAP> blk;
     memcpy(blk.v, recs, (size_t)nrec * kRecFloats * sizeof(float));
-    kernel<<<grid, THREADS, 0, st>>>(args, blk);
+    kernel<<<grid, THREADS, smem, st>>>(args, blk);
     return cudaGetLastError();
 }
 
@@ -433,58 +448,66 @@ static bool all_grey(const float* recs, int nrec) {
     return true;
 }
 
-// accurate-highlight variant (svbrdf_b200_loss_forward_backward_accurate): RenderingLoss forward+backward only
-template <typename T, bool GREY>
-static cudaError_t launch_loss_acc(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, true, false, GREY, false, kCapSmall, true>, grid, a, recs, nrec, st)
-                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, false, GREY, false, kCapLarge, true>, grid, a, recs, nrec, st);
+// Runtime axes of a loss launch that are template parameters of the kernel.
+struct LossSel {
+    bool grey;      // all records have r == g == b light colour
+    bool rowtab;    // per-warp row table in shared memory (packed lanes, W % 64 == 0, N <= kRowTabMaxN)
+    bool small;     // records fit the small parameter block
+};
+
+template <typename T, bool BWD, bool MIXED, bool ENC, bool ACC>
+static cudaError_t launch_loss_v(const LossSel& sel, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    constexpr int TH = Cfg<T>::kThreads;
+    constexpr bool kPacked = LaneTraits<T>::kLanes == 2;
+    const size_t smem = (size_t)(TH / 32) * 3 * a.N * sizeof(float4);
+#define SVB_GO(CAP, GREY, ROW) launch_with_scenes<CAP, TH>(loss_kernel<T, BWD, MIXED, GREY, ENC, CAP, ACC, ROW>, grid, a, recs, nrec, st, (ROW) ? smem : 0)
+    if constexpr (kPacked) {
+        if (sel.grey && sel.rowtab) {          // what RenderingLoss / MixedLoss launch on every power-of-two map size
+            if constexpr (ENC) return SVB_GO(kCapLarge, true, true);
+            else return sel.small ? SVB_GO(kCapSmall, true, true) : SVB_GO(kCapLarge, true, true);
+        }
+    }
+    if constexpr (ENC) return sel.grey ? SVB_GO(kCapLarge, true, false) : SVB_GO(kCapLarge, false, false);
+    else {
+        if (sel.grey) return sel.small ? SVB_GO(kCapSmall, true, false) : SVB_GO(kCapLarge, true, false);
+        return sel.small ? SVB_GO(kCapSmall, false, false) : SVB_GO(kCapLarge, false, false);
+    }
+#undef SVB_GO
 }
 
-template <typename T, bool BWD, bool MIXED, bool GREY>
-static cudaError_t launch_loss_g(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return small ? launch_with_scenes<kCapSmall, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapSmall>, grid, a, recs, nrec, st)
-                 : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, BWD, MIXED, GREY, false, kCapLarge>, grid, a, recs, nrec, st);
-}
-static inline bool aligned(const void* p, size_t n) { return ((uintptr_t)p & (n - 1)) == 0; }
-
-// encoded-input variant: always forward+backward, MixedLoss form, large parameter block
 template <typename T>
-static cudaError_t launch_loss_enc(dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return all_grey(recs, nrec)
-        ? launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, true, true, true, kCapLarge>, grid, a, recs, nrec, st)
-        : launch_with_scenes<kCapLarge, Cfg<T>::kThreads>(loss_kernel<T, true, true, false, true, kCapLarge>, grid, a, recs, nrec, st);
-}
-template <typename T, bool BWD, bool MIXED>
-static cudaError_t launch_loss(bool small, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    return all_grey(recs, nrec) ? launch_loss_g<T, BWD, MIXED, true>(small, grid, a, recs, nrec, st)
-                                : launch_loss_g<T, BWD, MIXED, false>(small, grid, a, recs, nrec, st);
-}
-template <typename T>
-static cudaError_t launch_loss_t(bool bwd, bool mixed, bool small, dim3 grid, const LossArgs& a, const float* recs,
-                                 int nrec, cudaStream_t st, bool accurate) {
-    if (accurate) return all_grey(recs, nrec) ? launch_loss_acc<T, true>(small, grid, a, recs, nrec, st)
-                                              : launch_loss_acc<T, false>(small, grid, a, recs, nrec, st);
-    if (bwd) return mixed ? launch_loss<T, true, true>(small, grid, a, recs, nrec, st)
-                          : launch_loss<T, true, false>(small, grid, a, recs, nrec, st);
-    return mixed ? launch_loss<T, false, true>(small, grid, a, recs, nrec, st)
-                 : launch_loss<T, false, false>(small, grid, a, recs, nrec, st);
+static cudaError_t launch_loss_t(bool bwd, bool mixed, bool encoded, bool accurate, const LossSel& sel, dim3 grid,
+                                 const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
+    if (encoded) return launch_loss_v<T, true, true, true, false>(sel, grid, a, recs, nrec, st);
+    if (accurate) return bwd ? launch_loss_v<T, true, false, false, true>(sel, grid, a, recs, nrec, st)
+                             : launch_loss_v<T, false, false, false, true>(sel, grid, a, recs, nrec, st);
+    if (bwd) return mixed ? launch_loss_v<T, true, true, false, false>(sel, grid, a, recs, nrec, st)
+                          : launch_loss_v<T, true, false, false, false>(sel, grid, a, recs, nrec, st);
+    return mixed ? launch_loss_v<T, false, true, false, false>(sel, grid, a, recs, nrec, st)
+                 : launch_loss_v<T, false, false, false, false>(sel, grid, a, recs, nrec, st);
 }
 
 // Enqueues the loss kernel for batch elements [b0, b0+bn) of a B-element problem (several launches if
-// the records do not fit one parameter block).  Pointers are for the WHOLE problem.
+// the records do not fit one parameter block).  Pointers are for the WHOLE problem; `packed` is
+// svb_loss_packed() of those pointers (the caller sizes the partial arrays with the same value).
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool encoded, bool accurate) {
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool packed, bool encoded,
+                          bool accurate) {
     const int cin = encoded ? 9 : 12;
-    const int cpi = svb_ctas_per_image(HW, W);
-    if (use_packed(W) && !(aligned(input, 8) && aligned(target, 8) && aligned(lin, 8) && (!grad || aligned(grad, 8))))
-        return fail(SVBRDF_E_INVALID, "device pointers must be 8-byte aligned when W is even");
+    const int cpi = svb_ctas_per_image(HW, packed);
     LossArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N;
     a.scale_render = (float)(1.0 / ((double)B * N * 3.0 * HW));
     a.scale_l1 = (float)((double)l1_weight / ((double)B * 3.0 * HW));
-    const bool small = !encoded && (size_t)bn * N <= (size_t)kCapSmall;
-    const int bc_max = balanced_chunk(bn, batch_per_launch(N, 1, small ? kCapSmall : kCapLarge));
+    LossSel sel;
+    sel.small = !encoded && (size_t)bn * N <= (size_t)kCapSmall;
+#ifdef SVB_NO_ROWTAB            // A/B builds (scripts/variant_bench.py)
+    sel.rowtab = false;
+#else
+    sel.rowtab = packed && (W % 64) == 0 && N <= kRowTabMaxN;
+#endif
+    const int bc_max = balanced_chunk(bn, batch_per_launch(N, 1, sel.small ? kCapSmall : kCapLarge));
     for (int s0 = b0; s0 < b0 + bn; s0 += bc_max) {
         const int bc = (b0 + bn - s0 < bc_max) ? (b0 + bn - s0) : bc_max;
         a.input = input + (size_t)s0 * cin * HW;
@@ -494,21 +517,18 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
         a.part_l1 = part_l1 + (size_t)s0 * cpi;
         const dim3 grid(cpi, bc);
         const float* recs = scenes + (size_t)s0 * N * kRecFloats;
-        cudaError_t e;
-        if (encoded)
-            e = use_packed(W) ? launch_loss_enc<F2>(grid, a, recs, bc * N, st) : launch_loss_enc<float>(grid, a, recs, bc * N, st);
-        else
-            e = use_packed(W) ? launch_loss_t<F2>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st, accurate)
-                              : launch_loss_t<float>(grad != nullptr, mixed, small, grid, a, recs, bc * N, st, accurate);
+        sel.grey = all_grey(recs, bc * N);
+        const cudaError_t e = packed ? launch_loss_t<F2>(grad != nullptr, mixed, encoded, accurate, sel, grid, a, recs, bc * N, st)
+                                     : launch_loss_t<float>(grad != nullptr, mixed, encoded, accurate, sel, grid, a, recs, bc * N, st);
         if (e != cudaSuccess) return cuda_status(e, "loss_kernel launch");
     }
     return 0;
 }
 
 // Adds the per-CTA partials of a B-element problem in a fixed order (fp64) and writes the loss value(s).
-int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, int W, int N, bool mixed,
+int svb_launch_finalize(const float* part_render, const float* part_l1, int B, int HW, bool packed, int N, bool mixed,
                         float l1_weight, float* out, int n_out, cudaStream_t st) {
-    const size_t total_ctas = (size_t)B * svb_ctas_per_image(HW, W);
+    const size_t total_ctas = (size_t)B * svb_ctas_per_image(HW, packed);
     // ln2 converts the log2 differences to natural log; 1/M is the mean of losses.py:50.
     const double mul_render = (double)kLn2 / ((double)B * N * 3.0 * HW);
     const double mul_l1 = 1.0 / ((double)B * 3.0 * HW);
@@ -529,14 +549,17 @@ static int loss_impl(const float* input, const float* target, int B, int H, int 
     if (int e = svb_check_shape(B, H, W, N)) return e;
     if (!input || !target || !scenes || !lin || !out || !ws) return fail(SVBRDF_E_INVALID, "null pointer argument");
     if (ws_bytes < svbrdf_b200_workspace_bytes(B, N, H, W)) return fail(SVBRDF_E_INVALID, "workspace too small");
+    if (((uintptr_t)input | (uintptr_t)target | (uintptr_t)lin | (uintptr_t)grad | (uintptr_t)ws | (uintptr_t)out) & 3u)
+        return fail(SVBRDF_E_INVALID, "device pointers must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
+    const bool packed = svb_loss_packed(W, input, target, grad, lin);
     float* part_render = (float*)ws;
-    float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, W);
+    float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, packed);
     if (int e = svb_launch_loss_range(input, target, grad, B, HW, W, scenes, N, lin, part_render, part_l1, mixed,
-                                      l1_weight, 0, B, st, encoded, accurate))
+                                      l1_weight, 0, B, st, packed, encoded, accurate))
         return e;
-    return svb_launch_finalize(part_render, part_l1, B, HW, W, N, mixed, l1_weight, out, n_out, st);
+    return svb_launch_finalize(part_render, part_l1, B, HW, packed, N, mixed, l1_weight, out, n_out, st);
 }
 
 extern "C" int svbrdf_b200_loss_forward(const float* input_dev, const float* target_dev, int B, int H, int W,
@@ -562,6 +585,13 @@ extern "C" int svbrdf_b200_loss_forward_backward_accurate(const float* input_dev
     if (!grad_input_dev) return fail(SVBRDF_E_INVALID, "grad_input_dev is null");
     return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, grad_input_dev,
                      workspace_dev, workspace_bytes, false, 0.f, stream, false, true);
+}
+
+extern "C" int svbrdf_b200_loss_forward_accurate(const float* input_dev, const float* target_dev, int B, int H, int W,
+                                                 const float* scenes_host, int N, const float* lin_dev, float* loss_dev,
+                                                 void* workspace_dev, size_t workspace_bytes, void* stream) {
+    return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, nullptr, workspace_dev,
+                     workspace_bytes, false, 0.f, stream, false, true);
 }
 
 extern "C" int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, const float* target_dev, int B, int H,
@@ -602,11 +632,11 @@ static int render_impl(const float* maps, int B, int H, int W, const float* scen
     if (!maps || !scenes || !lin) return fail(SVBRDF_E_INVALID, "null pointer argument");
     const bool backward = gmaps != nullptr;
     if (backward ? !gimages : !images) return fail(SVBRDF_E_INVALID, "null pointer argument");
+    if (((uintptr_t)maps | (uintptr_t)lin | (uintptr_t)images | (uintptr_t)gimages | (uintptr_t)gmaps) & 3u)
+        return fail(SVBRDF_E_INVALID, "device pointers must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int HW = H * W, cpi = svb_ctas_per_image(HW, W);
-    if (use_packed(W) && !(aligned(maps, 8) && aligned(lin, 8) && (!images || aligned(images, 8)) &&
-                           (!gimages || aligned(gimages, 8)) && (!gmaps || aligned(gmaps, 8))))
-        return fail(SVBRDF_E_INVALID, "device pointers must be 8-byte aligned when W is even");
+    const bool packed = (W & 1) == 0 && aligned8(maps) && aligned8(lin) && aligned8(images) && aligned8(gimages) && aligned8(gmaps);
+    const int HW = H * W, cpi = svb_ctas_per_image(HW, packed);
     RenderArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N; a.per_batch = per_batch ? 1 : 0;
     const size_t nrec_total = per_batch ? (size_t)B * N : (size_t)N;
@@ -621,8 +651,8 @@ static int render_impl(const float* maps, int B, int H, int W, const float* scen
         const dim3 grid(cpi, bc);
         const float* recs = per_batch ? scenes + (size_t)b0 * N * kRecFloats : scenes;
         const int nrec = per_batch ? bc * N : N;
-        const cudaError_t e = use_packed(W) ? launch_render_t<F2>(backward, small, grid, a, recs, nrec, st)
-                                            : launch_render_t<float>(backward, small, grid, a, recs, nrec, st);
+        const cudaError_t e = packed ? launch_render_t<F2>(backward, small, grid, a, recs, nrec, st)
+                                     : launch_render_t<float>(backward, small, grid, a, recs, nrec, st);
         if (e != cudaSuccess) return cuda_status(e, backward ? "render_bwd_kernel launch" : "render_fwd_kernel launch");
     }
     return 0;
@@ -648,19 +678,4 @@ extern "C" int svbrdf_b200_scale_grad(float* grad_dev, size_t count, const float
     if (blocks > 148 * 16) blocks = 148 * 16;
     scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_dev, count, upstream_dev);
     return cuda_status(cudaGetLastError(), "scale_kernel launch");
-}
-
-extern "C" int svbrdf_b200_probe_launch(int kind, int blocks, int iters, float* sink_dev, int* ops_per_thread_iter,
-                                        void* stream) {
-    if (blocks <= 0 || iters <= 0 || !sink_dev) return fail(SVBRDF_E_INVALID, "bad probe arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    int ops = 8 * 16;   // unroll 8 x 16 registers, one counted op each (an f32x2 instruction counts 2)
-    switch (kind) {
-        case 0: probe_kernel<0><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
-        case 1: probe_kernel<1><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
-        case 3: probe_kernel<3><<<blocks, 256, 0, st>>>(iters, sink_dev); break;
-        default: return fail(SVBRDF_E_INVALID, "unknown probe kind");
-    }
-    if (ops_per_thread_iter) *ops_per_thread_iter = ops;
-    return cuda_status(cudaGetLastError(), "probe_kernel launch");
 }

@@ -26,19 +26,28 @@ SVB_DEV bool same3(const float (&v)[12]) { return v[6] == v[7] && v[7] == v[8]; 
 SVB_DEV bool same3(const F2 (&v)[12]) {
     return lo(v[6]) == lo(v[7]) && lo(v[7]) == lo(v[8]) && hi(v[6]) == hi(v[7]) && hi(v[7]) == hi(v[8]);
 }
-// Do the inputs that feed colour channel C (normal, d_C, rough_C, s_C) differ between the two maps?
-template <int C>
-SVB_DEV bool chan_differs(const float (&a)[12], const float (&b)[12]) {
-    return a[0] != b[0] || a[1] != b[1] || a[2] != b[2] || a[3 + C] != b[3 + C] || a[6 + C] != b[6 + C] || a[9 + C] != b[9 + C];
+SVB_DEV bool vne(float a, float b) { return a != b; }
+SVB_DEV B2 vne(F2 a, F2 b) { return B2{lo(a) != lo(b), hi(a) != hi(b)}; }
+SVB_DEV bool vne1(float a) { return a != 1.f; }
+SVB_DEV B2 vne1(F2 a) { return B2{lo(a) != 1.f, hi(a) != 1.f}; }
+SVB_DEV bool mor(bool a, bool b) { return a || b; }
+SVB_DEV B2 mor(B2 a, B2 b) { return B2{a.x || b.x, a.y || b.y}; }
+SVB_DEV bool mand(bool a, bool b) { return a && b; }
+SVB_DEV B2 mand(B2 a, B2 b) { return B2{a.x && b.x, a.y && b.y}; }
+// Does colour channel C of the two maps RENDER differently?  Decided on the parameters the shading actually consumes:
+// the normal, the clamped roughness of the channel (two values below the clamp of renderers.py:87 are the same
+// material), the specular albedo, and the diffuse albedo unless the specular albedo is exactly 1 on both maps
+// ((1-F) d = 0 for any d then, renderers.py:18-20,32).  Where this is false the reference renders bit-identical values
+// and the channel contributes exactly 0 to the loss and to every gradient (sign(0) = 0, losses.py:50).
+template <typename T>
+SVB_DEV typename LaneTraits<T>::Mask normals_differ(const T (&a)[12], const T (&b)[12]) {
+    return mor(mor(vne(a[0], b[0]), vne(a[1], b[1])), vne(a[2], b[2]));
 }
-template <int C>
-SVB_DEV B2 chan_differs(const F2 (&a)[12], const F2 (&b)[12]) {
-    B2 d;
-    d.x = lo(a[0]) != lo(b[0]) || lo(a[1]) != lo(b[1]) || lo(a[2]) != lo(b[2]) || lo(a[3 + C]) != lo(b[3 + C]) ||
-          lo(a[6 + C]) != lo(b[6 + C]) || lo(a[9 + C]) != lo(b[9 + C]);
-    d.y = hi(a[0]) != hi(b[0]) || hi(a[1]) != hi(b[1]) || hi(a[2]) != hi(b[2]) || hi(a[3 + C]) != hi(b[3 + C]) ||
-          hi(a[6 + C]) != hi(b[6 + C]) || hi(a[9 + C]) != hi(b[9 + C]);
-    return d;
+template <typename T>
+SVB_DEV typename LaneTraits<T>::Mask rough_differs(T ra, T rb) { return vne(vmax(ra, kClamp), vmax(rb, kClamp)); }
+template <typename T>
+SVB_DEV typename LaneTraits<T>::Mask albedo_differs(T da, T sa, T db, T sb) {
+    return mor(vne(sa, sb), mand(vne(da, db), mor(vne1(sa), vne1(sb))));
 }
 SVB_DEV bool all_or_none(bool a, bool b, bool c) { return (a == b) && (b == c); }
 SVB_DEV bool all_or_none(B2 a, B2 b, B2 c) { return (a.x == b.x) && (b.x == c.x) && (a.y == b.y) && (b.y == c.y); }
@@ -49,16 +58,16 @@ SVB_DEV bool all_or_none(B2 a, B2 b, B2 c) { return (a.x == b.x) && (b.x == c.x)
 // C0 = first colour channel of the pass (0 for NC = 3; the pass's channel for NC = 1).
 // GREY: every record of the launch has r == g == b light colour (always true for the scenes
 // RenderingLoss samples, environment.py:27,52), so colour * falloff is formed once, not per channel.
+// RS: the record source (shading.cuh ConstRecs, or the kernels' per-warp shared-memory table).
 // Returns sum |log2 ratio| (ln2 and the mean are applied to the reduced loss).
 // ACC: accurate-highlight GGX denominator in both forward evaluations (shading.cuh shade_fwd<..., ACC>).
-template <typename T, int NC, int C0, bool BWD, bool GREY, bool ACC = false>
-SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y, const float* __restrict__ rec, int N,
-                       Acc<T, NC>& acc) {
+template <typename T, int NC, int C0, bool BWD, bool GREY, bool ACC, typename RS>
+SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, const RS& recs, int N, Acc<T, NC>& acc) {
     T lsum = LaneTraits<T>::splat(0.f);
     SVB_UNROLL1
     for (int k = 0; k < N; ++k) {
-        const float* __restrict__ rk = rec + k * kRecFloats;
-        const Geo<T> g = make_geo<T>(x, y, rk);
+        const RecScalars rk = recs.get(k);
+        const Geo<T> g = make_geo<T>(x, rk);
         Fwd<T> fi, ft;
 #ifdef SVB_ACCURATE_LOSS       // build option: accurate form in every loss kernel (~ +13 % time)
         constexpr bool kAcc = true;
@@ -70,7 +79,7 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
         // radiance + 0.1 of both maps (losses.py:46-47); E = light colour * falloff / pi
         T E[NC], fin[NC], xi[NC], xt[NC];
         if (GREY) {
-            E[0] = g.fall * (rk[6 + C0] * kInvPi);
+            E[0] = g.fall * rk.col[C0];
             radiance_plus_eps_grey<T, NC>(g, pt, ft, E[0] * ft.LN0, kEpsRender, xt);
             if (BWD) {                                                     // the gradient of LN0 needs f' itself
                 brdf_values<T, NC>(g, pi, fi, fin);
@@ -86,7 +95,7 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
             brdf_values<T, NC>(g, pt, ft, ftg);
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                E[c] = g.fall * (rk[6 + C0 + c] * kInvPi);
+                E[c] = g.fall * rk.col[C0 + c];
                 xi[c] = vfma(fin[c], E[c] * fi.LN0, kEpsRender);
                 xt[c] = vfma(ftg[c], E[c] * ft.LN0, kEpsRender);
             }
@@ -99,8 +108,8 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
             const T l = vlg2(xt[c] * ix);
             lsum = lsum + vabs(l);
             // d|l|/d xi = -sign(l)/xi: the accumulators carry +sign(l)/xi and the caller applies the minus
-            // with the final scale.  sign(0) is taken as +1 here: an exact 0 only arises from inputs that
-            // are bitwise identical for this channel, and those are masked in loss_pixel (losses.py:50).
+            // with the final scale.  sign(0) is taken as +1 here: an exact 0 only arises from channels that
+            // render identically, and those are masked in loss_pixel (losses.py:50).
             if (BWD) A[c] = vcopysign(ix, l);
         }
         if (BWD) {
@@ -127,16 +136,18 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, float y,
     return lsum;
 }
 
-// One single-channel pass (general path): channel C of input/target with its own roughness.  `live`
-// masks lanes whose channel-C inputs are bitwise identical (their exact contribution is 0).
-template <typename T, int C, bool BWD, bool GREY, bool ACC = false>
-SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
-                            float nscale, typename LaneTraits<T>::Mask live, T (&g)[12]) {
+// One single-channel pass (general path): channel C of input/target with its own roughness.  Lanes whose
+// channel-C parameters render identically are masked (their exact contribution is 0).
+template <typename T, int C, bool BWD, bool GREY, bool ACC, typename RS>
+SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, const RS& recs, int N,
+                            float nscale, typename LaneTraits<T>::Mask ndiff, T (&g)[12]) {
+    const typename LaneTraits<T>::Mask live =
+        mor(mor(ndiff, rough_differs<T>(vi[6 + C], vt[6 + C])), albedo_differs<T>(vi[3 + C], vi[9 + C], vt[3 + C], vt[9 + C]));
     const Pix<T, 1> pi = make_pix<T, 1>(&vi[0], &vi[3 + C], &vi[9 + C], vi[6 + C]);
     const Pix<T, 1> pt = make_pix<T, 1>(&vt[0], &vt[3 + C], &vt[9 + C], vt[6 + C]);
     Acc<T, 1> acc;
     acc_zero(acc);
-    const T l = loss_records<T, 1, C, BWD, GREY, ACC>(pi, pt, x, y, rec, N, acc);
+    const T l = loss_records<T, 1, C, BWD, GREY, ACC, RS>(pi, pt, x, recs, N, acc);
     if (BWD) {
         const T ns = vsel(live, LaneTraits<T>::splat(nscale), 0.f);    // masked lanes: scale 0
         T gd[1], gs[1];
@@ -152,27 +163,29 @@ SVB_DEV T loss_channel_pass(const T (&vi)[12], const T (&vt)[12], T x, float y, 
 
 // Loss (log2 units, unscaled) and d loss / d input (scaled by `scale`) of one thread's pixels.
 //
-// Exact zeros: where the inputs feeding a colour channel are bitwise identical in input and target the
-// reference renders identical values and that channel contributes exactly 0 to the loss and to every
-// gradient.  Here input and target run through differently scheduled instruction sequences, so that
-// case is handled explicitly: the fast path requires that, per pixel, either all three channels differ
-// or none does (fully identical pixels are zeroed at the end); anything else takes the channel-wise path
-// where identical channels are masked.
-template <typename T, bool BWD, bool GREY, bool ACC = false>
-SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
-                     float scale, T (&g)[12]) {
+// Exact zeros: where a colour channel of the two maps renders identically (see albedo_differs above) the reference
+// produces identical values and that channel contributes exactly 0 to the loss and to every gradient.  Here input
+// and target run through differently scheduled instruction sequences, so that case is handled explicitly: the fast
+// path requires that, per pixel, either all three channels differ or none does (identical pixels are zeroed at
+// the end); anything else takes the channel-wise path where identical channels are masked.
+template <typename T, bool BWD, bool GREY, bool ACC, typename RS>
+SVB_DEV T loss_pixel_rs(const T (&vi)[12], const T (&vt)[12], T x, const RS& recs, int N, float scale, T (&g)[12]) {
     typedef typename LaneTraits<T>::Mask M;
-    const M d0 = chan_differs<0>(vi, vt), d1 = chan_differs<1>(vi, vt), d2 = chan_differs<2>(vi, vt);
+    const M ndiff = normals_differ<T>(vi, vt);
     const float nscale = -scale;    // the accumulators carry the gradient with the opposite sign (loss_records)
     // fast path: the warp's pixels all carry one roughness value replicated on the three channels
+    const M common = mor(ndiff, rough_differs<T>(vi[6], vt[6]));
+    const M d0 = mor(common, albedo_differs<T>(vi[3], vi[9], vt[3], vt[9]));
+    const M d1 = mor(common, albedo_differs<T>(vi[4], vi[10], vt[4], vt[10]));
+    const M d2 = mor(common, albedo_differs<T>(vi[5], vi[11], vt[5], vt[11]));
     if (SVB_WARP_ALL(same3(vi) && same3(vt) && all_or_none(d0, d1, d2))) {
         const Pix<T, 3> pi = make_pix<T, 3>(&vi[0], &vi[3], &vi[9], vi[6]);
         const Pix<T, 3> pt = make_pix<T, 3>(&vt[0], &vt[3], &vt[9], vt[6]);
         Acc<T, 3> acc;
         acc_zero(acc);
-        const T l = loss_records<T, 3, 0, BWD, GREY, ACC>(pi, pt, x, y, rec, N, acc);
+        const T l = loss_records<T, 3, 0, BWD, GREY, ACC, RS>(pi, pt, x, recs, N, acc);
         if (BWD) {
-            const T ns = vsel(d0, LaneTraits<T>::splat(nscale), 0.f);  // fully identical pixels: scale 0
+            const T ns = vsel(d0, LaneTraits<T>::splat(nscale), 0.f);  // identically rendering pixels: scale 0
             const T chain = rough_chain(vi[6]) * ns;
             T gd[3], gs[3];
             acc_albedo_grads<T, 3>(acc, &vi[3], &vi[9], gd, gs);
@@ -188,10 +201,17 @@ SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const f
     }
     // general path: three single-channel passes (the loss and all gradients decompose by colour channel)
     if (BWD) { g[0] = g[1] = g[2] = LaneTraits<T>::splat(0.f); }
-    T l = loss_channel_pass<T, 0, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d0, g);
-    l = l + loss_channel_pass<T, 1, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d1, g);
-    l = l + loss_channel_pass<T, 2, BWD, GREY, ACC>(vi, vt, x, y, rec, N, nscale, d2, g);
+    T l = loss_channel_pass<T, 0, BWD, GREY, ACC, RS>(vi, vt, x, recs, N, nscale, ndiff, g);
+    l = l + loss_channel_pass<T, 1, BWD, GREY, ACC, RS>(vi, vt, x, recs, N, nscale, ndiff, g);
+    l = l + loss_channel_pass<T, 2, BWD, GREY, ACC, RS>(vi, vt, x, recs, N, nscale, ndiff, g);
     return l;
+}
+// records read where the launcher put them (kernel parameter block; host memory in the emulation)
+template <typename T, bool BWD, bool GREY, bool ACC = false>
+SVB_DEV T loss_pixel(const T (&vi)[12], const T (&vt)[12], T x, float y, const float* __restrict__ rec, int N,
+                     float scale, T (&g)[12]) {
+    const ConstRecs recs{rec, y};
+    return loss_pixel_rs<T, BWD, GREY, ACC, ConstRecs>(vi, vt, x, recs, N, scale, g);
 }
 
 // Map-space L1 terms of SVBRDFL1Loss (losses.py:7-19) for one thread's pixels (natural-log units,

@@ -175,19 +175,42 @@ struct Geo {
     T hx, hy, hz, ih2; // wi + wo and 1 / |wi + wo|^2 (only the accurate-highlight forward reads them)
 };
 
-// s points at one scene record (9 floats: camera xyz, light xyz, colour rgb) in the constant bank.
-// x is per lane; y is the row coordinate (the lanes of an F2 are horizontal neighbours).
+// What one scene record (9 floats: camera xyz, light xyz, colour rgb) contributes that is the same for every pixel
+// of an image ROW: the y/z parts of the vectors to the light and to the camera.  The kernels either form it per
+// thread from the constant bank (ConstRecs) or once per warp into shared memory (RowTabRecs, kernels.cu) - both
+// with exactly these operations, so the two paths are bit-identical.
+struct RecScalars {
+    float sx, vx;          // light x, camera x
+    float ly, lz, lyz;     // light - p: y and z components, ly^2 + lz^2
+    float vy, vz, vyz;     // camera - p
+    float col[3];          // light colour / pi
+};
+SVB_DEV RecScalars rec_scalars(const float* __restrict__ s, float y) {
+    RecScalars r;
+    r.sx = s[3]; r.vx = s[0];
+    r.ly = s[4] - y; r.lz = s[5]; r.vy = s[1] - y; r.vz = s[2];
+    r.lyz = fmaf(r.ly, r.ly, r.lz * r.lz); r.vyz = fmaf(r.vy, r.vy, r.vz * r.vz);
+    r.col[0] = s[6] * kInvPi; r.col[1] = s[7] * kInvPi; r.col[2] = s[8] * kInvPi;
+    return r;
+}
+// Record source reading the records where the launcher put them (kernel parameter block / host memory).
+struct ConstRecs {
+    const float* rec;      // [N,9]
+    float y;               // row coordinate of this thread's pixel(s)
+    SVB_DEV RecScalars get(int k) const { return rec_scalars(rec + k * 9, y); }
+};
+
+// x is per lane; the row coordinate is inside r (the lanes of an F2 are horizontal neighbours).
 template <typename T>
-SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
+SVB_DEV Geo<T> make_geo(T x, const RecScalars& r) {
     Geo<T> g;
-    const float ly = s[4] - y, lz = s[5], vy = s[1] - y, vz = s[2];
-    const float lyz = fmaf(ly, ly, lz * lz), vyz = fmaf(vy, vy, vz * vz);     // shared by the lanes
-    const T lx = LaneTraits<T>::splat(s[3]) - x;
-    const T il = vrsqrt(vfma(lx, lx, lyz));
+    const float ly = r.ly, lz = r.lz, vy = r.vy, vz = r.vz;
+    const T lx = LaneTraits<T>::splat(r.sx) - x;
+    const T il = vrsqrt(vfma(lx, lx, r.lyz));
     g.wix = lx * il; g.wiy = il * ly; g.wiz = il * lz;
     g.fall = il * il;
-    const T vx = LaneTraits<T>::splat(s[0]) - x;
-    const T iv = vrsqrt(vfma(vx, vx, vyz));
+    const T vx = LaneTraits<T>::splat(r.vx) - x;
+    const T iv = vrsqrt(vfma(vx, vx, r.vyz));
     g.wox = vx * iv; g.woy = iv * vy; g.woz = iv * vz;
     // |wi+wo| from the summed vector itself (not from 2 + 2 wi.wo): the rounding of the two
     // normalisations then cancels in n.h to first order exactly where the GGX lobe is sharpest
@@ -204,6 +227,9 @@ SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) {
     g.ih2 = g.ih * g.ih;
     return g;
 }
+// s points at one scene record in the constant bank / host memory
+template <typename T>
+SVB_DEV Geo<T> make_geo(T x, float y, const float* __restrict__ s) { return make_geo<T>(x, rec_scalars(s, y)); }
 
 // ---- per pixel: quantities of one SVBRDF map that do not depend on the scene record ----------
 // Scaling convention: everything below works with f' = pi * f (BRDF value times pi) so that the

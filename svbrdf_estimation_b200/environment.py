@@ -128,19 +128,10 @@ def _affine_like_torch(raw, lo, hi):
     return (raw.double() * float(hi32 - lo32) + float(lo32)).float()
 
 
-def sample_loss_configs(batch, n_random=3, n_specular=6):
-    """Scene records of one ``RenderingLoss.forward`` call: for each batch element, ``n_random``
-    random then ``n_specular`` mirror configurations (losses.py:34-35) -> [batch, N, 9] float32 CPU.
-
-    The global CPU generator is consumed in exactly the reference's order (a seed reproduces the
-    reference's scenes bit for bit, tests/golden/scenes.npz), but with 2-3 generator calls per batch
-    element instead of 9: consecutive ``uniform_`` draws are taken as one raw ``uniform_(0, 1)`` block and
-    mapped to their ranges afterwards, and the two ``normal_`` draws are merged while that keeps ATen on its
-    scalar sampling path (fewer than 16 values).  The trigonometry runs once over the whole block."""
-    nr, ns = int(n_random), int(n_specular)
-    head, tail = 4 * nr + 2 * ns, 2 * ns            # per element: [view/light r1 r2 | spec r1 r2] ... normals ... [shift]
-    if batch <= 0 or nr + ns <= 0:
-        raise ValueError("batch and the number of configurations must be positive")
+def _draws_through_torch(batch, nr, ns, head, tail):
+    """The raw draws of one loss evaluation through torch's own generator calls: 2-3 calls per batch element (consecutive
+    ``uniform_`` draws are taken as one raw ``uniform_(0, 1)`` block, the two ``normal_`` draws are merged while that
+    keeps ATen on its scalar sampling path)."""
     uni = torch.empty(batch, head + tail)
     nrm = torch.empty(batch, 2, ns)
     # uniform blocks in stream order: element 0's directions, then (shift of b + directions of b+1), last shift
@@ -159,6 +150,51 @@ def sample_loss_configs(batch, n_random=3, n_specular=6):
             nblocks[b * per_elem + j].normal_(mean, std)
         if sizes[b + 1] > 0:
             ublocks[b + 1].uniform_(0.0, 1.0)
+    return uni, nrm
+
+
+def _records_native(batch, nr, ns):
+    """Scene records through the library's restatement of ATen's CPU generator and of the samplers' float arithmetic
+    (csrc/scene_sampler.cpp): the draws of the whole batch come from ONE call on the serialised generator state, which
+    is stored back so torch continues where the reference would; sqrt / cos / sin / exp are torch's own, applied once to the
+    whole batch, so every value is rounded exactly as in the reference."""
+    from . import _cabi
+    lib = _cabi.lib()
+    nd = 2 * nr + ns
+    state = torch.get_rng_state()
+    r1, phi = torch.empty(batch, nd), torch.empty(batch, nd)
+    logd, shift = torch.empty(batch, 2, ns), torch.empty(batch, ns, 2)
+    _cabi.check(lib.svbrdf_b200_reference_scenes_begin(state.data_ptr(), state.numel(), batch, nr, ns, r1.data_ptr(),
+                                                       phi.data_ptr(), logd.data_ptr(), shift.data_ptr()))
+    torch.set_rng_state(state)
+    radius = torch.sqrt(r1)                                                         # utils.py:104
+    cos_phi, sin_phi = torch.cos(phi), torch.sin(phi)                               # utils.py:107-108
+    z = torch.sqrt(1.0 - radius * radius)                                           # utils.py:109
+    dist = torch.exp(logd)                                                          # environment.py:38-39
+    out = torch.empty(batch, nr + ns, 9)
+    _cabi.check(lib.svbrdf_b200_reference_scenes_finish(batch, nr, ns, radius.data_ptr(), cos_phi.data_ptr(), sin_phi.data_ptr(),
+                                                        z.data_ptr(), dist.data_ptr(), shift.data_ptr(), out.data_ptr()))
+    return out
+
+
+def sample_loss_configs(batch, n_random=3, n_specular=6, native_draws=True):
+    """Scene records of one ``RenderingLoss.forward`` call: for each batch element, ``n_random``
+    random then ``n_specular`` mirror configurations (losses.py:34-35) -> [batch, N, 9] float32 CPU.
+
+    The global CPU generator is consumed in exactly the reference's order (a seed reproduces the
+    reference's scenes bit for bit, tests/golden/scenes.npz, and the generator is left in the state the
+    reference would leave it in).  ``native_draws``: the library's restatement of ATen's mt19937 / uniform /
+    normal sampling and of the samplers' float arithmetic does the whole batch in two C calls around three torch
+    ops (~0.1 ms for 64 elements; the reference's own loop takes 23 ms).  Otherwise - and whenever ``normal_``
+    would take ATen's vectorised path, n_specular >= 16 - the draws go through torch's generator calls, 2-3 per
+    batch element, and the arithmetic through batched torch ops."""
+    nr, ns = int(n_random), int(n_specular)
+    if batch <= 0 or nr + ns <= 0:
+        raise ValueError("batch and the number of configurations must be positive")
+    if native_draws and ns < 16:
+        return _records_native(batch, nr, ns)
+    head, tail = 4 * nr + 2 * ns, 2 * ns            # per element: [view/light r1 r2 | spec r1 r2] ... normals ... [shift]
+    uni, nrm = _draws_through_torch(batch, nr, ns, head, tail)
     plan = _sampler_plan(nr, ns)
     # every uniform_(lo, hi) of the reference as ATen computes it from the raw draw: x*(hi-lo)+lo with x in
     # double, (hi-lo) in float, one rounding to float (uniform_real_distribution) - for all columns at once

@@ -52,11 +52,14 @@ def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded
                 a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, float(l1_weight), lin.data_ptr(),
                 out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream)
         elif accurate:
-            # accurate-highlight evaluation (RenderingLoss only); it always writes the gradient
-            scratch = grad if grad is not None else torch.empty_like(a)
-            status = lib.svbrdf_b200_loss_forward_backward_accurate(
-                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
-                scratch.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+            fn = lib.svbrdf_b200_loss_forward_backward_accurate if grad is not None else None
+            if fn is not None:
+                status = fn(a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
+                            gp, ws.data_ptr(), ws_bytes, stream)
+            else:
+                status = lib.svbrdf_b200_loss_forward_accurate(
+                    a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
+                    ws.data_ptr(), ws_bytes, stream)
         elif grad is not None:
             status = lib.svbrdf_b200_loss_forward_backward(
                 a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(), gp,
@@ -69,32 +72,39 @@ def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded
 
 
 class _FusedLoss(torch.autograd.Function):
-    """Loss value and - computed in the same kernel pass - d loss / d input for given host scene records.
+    """Loss value and d loss / d input for given host scene records.
 
     ``l1_weight is None`` -> RenderingLoss, otherwise MixedLoss with that weight; ``encoded`` -> ``input`` is
-    the 9-channel network output.  Returns ``(loss, parts)``: ``loss`` is the differentiable 0-dim value,
-    ``parts = [rendering loss, map-L1 loss]`` is informational and marked non-differentiable."""
+    the 9-channel network output.  ``eager``: the gradient is computed by the same kernel pass as the loss value
+    (training: one launch for forward + backward) and handed to autograd on the first ``backward()``.  Without
+    ``eager`` (validation) the forward-only kernel runs and nothing is allocated for a gradient; if ``backward()`` is
+    called after all - or a second time with ``retain_graph=True`` - the gradient is recomputed then.
+    Returns ``(loss, parts)``: ``loss`` is the differentiable 0-dim value, ``parts = [rendering loss, map-L1
+    loss]`` is informational and marked non-differentiable."""
 
     @staticmethod
-    def forward(ctx, input, target, records, l1_weight, encoded, accurate=False):
+    def forward(ctx, input, target, records, l1_weight, encoded, accurate=False, eager=True):
         B, _, H, W = target.shape
         dev = target.device
+        if accurate and (l1_weight is not None or encoded):
+            raise NotImplementedError("accurate=True is available for RenderingLoss (not MixedLoss / encoded input)")
         out = torch.empty(3, device=dev, dtype=torch.float32)
         ws, ws_bytes = _workspace(B, records.shape[1], H, W, dev)
         lin = coordinate_table(W, dev)
         want_in, want_tg = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        grad_in = torch.empty_like(input) if (want_in or encoded) else None
-        if accurate and (l1_weight is not None or encoded):
-            raise NotImplementedError("accurate=True is available for RenderingLoss (not MixedLoss / encoded input)")
+        if want_tg and encoded:
+            raise NotImplementedError("the gradient w.r.t. the target is not available for encoded input")
+        # the encoded-input kernels only exist in the forward+backward form
+        grad_in = torch.empty_like(input) if ((want_in and eager) or encoded) else None
         _launch_loss(input, target, records, l1_weight, out, grad_in, ws, ws_bytes, lin, encoded, accurate)
         grad_tg = None
-        if want_tg:
-            if encoded:
-                raise NotImplementedError("the gradient w.r.t. the target is not available for encoded input")
+        if want_tg and eager:
             # the loss is symmetric in its arguments: d/d target = the same kernel with the roles swapped
             grad_tg = torch.empty_like(target)
             _launch_loss(target, input, records, l1_weight, torch.empty_like(out), grad_tg, ws, ws_bytes, lin, False, accurate)
-        ctx.grads = (grad_in if want_in else None, grad_tg)
+        ctx.grads = (grad_in if want_in else None, grad_tg) if eager else None
+        ctx.save_for_backward(input, target)
+        ctx.records, ctx.meta = records, (l1_weight, encoded, accurate)
         loss, parts = out[0].reshape(()), out[1:3]
         if l1_weight is None:
             parts = torch.stack((loss.detach(), torch.zeros_like(loss)))
@@ -102,11 +112,26 @@ class _FusedLoss(torch.autograd.Function):
         return loss, parts
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_parts):
-        if ctx.grads is None:
-            raise RuntimeError("the fused rendering loss was already back-propagated; its gradient buffer "
-                               "is handed to autograd on the first backward()")
+        want_in, want_tg = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         grads, ctx.grads = ctx.grads, None
+        if grads is None:
+            # validation-mode forward, or a repeated backward (retain_graph=True): evaluate the gradient now
+            input, target = ctx.saved_tensors
+            l1_weight, encoded, accurate = ctx.meta
+            B, _, H, W = target.shape
+            ws, ws_bytes = _workspace(B, ctx.records.shape[1], H, W, target.device)
+            lin = coordinate_table(W, target.device)
+            scratch = torch.empty(3, device=target.device, dtype=torch.float32)
+            g_in = g_tg = None
+            if want_in:
+                g_in = torch.empty_like(input)
+                _launch_loss(input, target, ctx.records, l1_weight, scratch, g_in, ws, ws_bytes, lin, encoded, accurate)
+            if want_tg:
+                g_tg = torch.empty_like(target)
+                _launch_loss(target, input, ctx.records, l1_weight, scratch, g_tg, ws, ws_bytes, lin, False, accurate)
+            grads = (g_in, g_tg)
         up = grad_loss.reshape(1).to(torch.float32).contiguous()
         lib = _cabi.lib()
         for g in grads:
@@ -115,10 +140,10 @@ class _FusedLoss(torch.autograd.Function):
                     # in place; returns on the device when the upstream gradient is 1 (no host sync)
                     _cabi.check(lib.svbrdf_b200_scale_grad(g.data_ptr(), g.numel(), up.data_ptr(),
                                                            torch.cuda.current_stream().cuda_stream))
-        return grads[0], grads[1], None, None, None, None
+        return grads[0], grads[1], None, None, None, None, None
 
 
-def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1):
+def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1, eager=True):
     """``MixedLoss`` evaluated directly on the network's encoded output ``[B,9,H,W]`` (after tanh: normal xy,
     diffuse, roughness, specular in [-1,1]); the decode of models.py:334-346 / utils.py:73-98 and its chain
     rule run inside the loss kernel (SURVEY.md 8f-3).  Returns ``(mixed, rendering, map_l1)`` 0-dim tensors;
@@ -130,33 +155,36 @@ def mixed_loss_from_encoded(encoded, target, records, l1_weight=0.1):
     b, _, origin = as_device_maps(target, "target")
     if tuple(encoded.shape[0:1] + encoded.shape[2:]) != tuple(b.shape[0:1] + b.shape[2:]):
         raise ValueError("encoded %s and target %s do not match" % (tuple(encoded.shape), tuple(target.shape)))
-    e = (encoded if encoded.is_cuda else encoded.cuda()).contiguous()
+    if encoded.is_cuda and encoded.device != b.device:
+        raise ValueError("encoded is on %s, target on %s" % (encoded.device, b.device))
+    e = encoded.to(b.device).contiguous()
     rec = as_host_records(records, b.shape[0])
     if rec.dim() != 3:
         raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
-    loss, parts = _FusedLoss.apply(e, b, rec, float(l1_weight), True, False)
-    out = (loss, parts[0], parts[1])
-    return out if origin.type == "cuda" else tuple(t.to(origin) for t in out)
+    loss, parts = _FusedLoss.apply(e, b, rec, float(l1_weight), True, False, bool(eager))
+    return tuple(origin.restore(t) for t in (loss, parts[0], parts[1]))
 
 
-def _fused_loss(input, target, records, l1_weight, accurate=False):
+def _fused_loss(input, target, records, l1_weight, accurate=False, eager=True):
     """-> differentiable 0-dim loss on the input's device (RenderingLoss, or MixedLoss when l1_weight is given)."""
     _check_pair(input, target)
     a, _, origin = as_device_maps(input, "input")
     b, _, _ = as_device_maps(target, "target")
+    if a.device != b.device:
+        raise ValueError("input and target are on different devices")
     rec = as_host_records(records, a.shape[0])
     if rec.dim() != 3:
         raise ValueError("the loss needs per-batch-element scene records [B,N,9]")
-    loss, _ = _FusedLoss.apply(a, b, rec, l1_weight, False, bool(accurate))
-    return loss if origin.type == "cuda" else loss.to(origin)
+    loss, _ = _FusedLoss.apply(a, b, rec, l1_weight, False, bool(accurate), bool(eager))
+    return origin.restore(loss)
 
 
-def rendering_loss_with_records(input, target, records, accurate=False):
+def rendering_loss_with_records(input, target, records, accurate=False, eager=True):
     """``RenderingLoss`` for explicit scene records ``[B,N,9]`` (no sampling) - the notebook-style
     fixed-scene loss and the form the parity tests use.  ``accurate=True`` selects the accurate-highlight
     kernels (loss and gradient 20-30x closer to an fp64 evaluation than the reference's own fp32 run,
     about 12 % slower)."""
-    return _fused_loss(input, target, records, None, accurate)
+    return _fused_loss(input, target, records, None, accurate, eager)
 
 
 class SVBRDFL1Loss(nn.Module):
@@ -192,9 +220,12 @@ class RenderingLoss(nn.Module):
         return sampler(batch_size, self.random_configuration_count, self.specular_configuration_count)
 
     def forward(self, input, target):
+        """In training mode (the default of every ``nn.Module``) the gradient w.r.t. ``input`` comes out of the same
+        kernel pass as the value.  After ``.eval()`` only the value is computed (validation, main.py:140); a
+        ``backward()`` still works and evaluates the gradient then."""
         if getattr(self.renderer, "fused_rendering_loss", False):
             _check_pair(input, target)
-            return _fused_loss(input, target, self.sample_records(input.shape[0]), None, self.accurate)
+            return _fused_loss(input, target, self.sample_records(input.shape[0]), None, self.accurate, self.training)
         return self._forward_with_plugin(input, target)
 
     def _forward_with_plugin(self, input, target):
@@ -225,7 +256,7 @@ class MixedLoss(nn.Module):
         rl = self.rendering_loss
         if getattr(rl.renderer, "fused_rendering_loss", False):
             _check_pair(input, target)
-            return _fused_loss(input, target, rl.sample_records(input.shape[0]), float(self.l1_weight))
+            return _fused_loss(input, target, rl.sample_records(input.shape[0]), float(self.l1_weight), False, self.training)
         return self.l1_weight * self.l1_loss(input, target) + rl(input, target)
 
     def forward_encoded(self, encoded, target):
@@ -235,7 +266,7 @@ class MixedLoss(nn.Module):
         if not getattr(rl.renderer, "fused_rendering_loss", False):
             from .utils import decode_network_output
             return self.forward(decode_network_output(encoded), target)
-        return mixed_loss_from_encoded(encoded, target, rl.sample_records(target.shape[0]), float(self.l1_weight))[0]
+        return mixed_loss_from_encoded(encoded, target, rl.sample_records(target.shape[0]), float(self.l1_weight), self.training)[0]
 
 
 __all__ = ["SVBRDFL1Loss", "RenderingLoss", "MixedLoss", "rendering_loss_with_records", "mixed_loss_from_encoded"]

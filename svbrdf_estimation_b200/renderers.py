@@ -32,9 +32,25 @@ def require_cuda():
         raise RuntimeError("svbrdf_estimation_b200 needs a CUDA device: the rendering path has no CPU fallback")
 
 
+class Origin:
+    """Where a caller's tensor lived and in which dtype, so results can follow it (the reference's outputs have the
+    device and dtype of its inputs, renderers.py:68)."""
+    __slots__ = ("device", "dtype")
+
+    def __init__(self, device, dtype):
+        self.device, self.dtype = device, dtype
+
+    def restore(self, t):
+        """Result tensor -> the caller's device; float64 callers get float64 back (computed in fp32)."""
+        if self.device.type != "cuda":
+            t = t.to(self.device)
+        return t.to(torch.float64) if self.dtype == torch.float64 else t
+
+
 def as_device_maps(svbrdf, what="svbrdf"):
     """Validate a packed SVBRDF tensor and return (maps[B,12,H,W] fp32 contiguous on CUDA,
-    leading shape, original device)."""
+    leading shape, Origin).  The kernels compute in fp32: half-precision maps (a network output under autocast)
+    are upcast, float64 maps are computed in fp32 and the results returned as float64."""
     if not isinstance(svbrdf, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % what)
     if svbrdf.dim() < 3 or svbrdf.shape[-3] != 12:
@@ -42,18 +58,27 @@ def as_device_maps(svbrdf, what="svbrdf"):
     if svbrdf.shape[-1] != svbrdf.shape[-2]:
         raise ValueError("only square maps are supported (renderers.py:73-76), got %dx%d"
                          % (svbrdf.shape[-2], svbrdf.shape[-1]))
-    if svbrdf.dtype in (torch.float16, torch.bfloat16):
-        svbrdf = svbrdf.float()          # e.g. a network output under autocast: the kernels compute in fp32
-    if svbrdf.dtype != torch.float32:
-        raise TypeError("%s must be float32 (the kernels compute in fp32), got %s" % (what, svbrdf.dtype))
+    if not svbrdf.dtype.is_floating_point:
+        raise TypeError("%s must be a floating-point tensor, got %s" % (what, svbrdf.dtype))
     require_cuda()
-    origin = svbrdf.device
+    origin = Origin(svbrdf.device, svbrdf.dtype)
     lead = tuple(svbrdf.shape[:-3])
-    maps = svbrdf if origin.type == "cuda" else svbrdf.cuda()
+    if svbrdf.dtype != torch.float32:
+        svbrdf = svbrdf.float()          # differentiable: the gradient comes back in the caller's dtype
+    maps = svbrdf if origin.device.type == "cuda" else host_to_device(svbrdf)
     maps = maps.reshape((-1,) + tuple(svbrdf.shape[-3:])).contiguous()
     if maps.shape[0] == 0:
         raise ValueError("%s has an empty batch" % what)
     return maps, lead, origin
+
+
+def host_to_device(t):
+    """Host tensor -> current CUDA device (differentiable).  Small tensors and pinned tensors are one copy; large
+    pageable tensors go through ``staging.upload`` (pinned double buffer, CPU copy overlapped with the DMA)."""
+    if t.requires_grad or t.numel() * t.element_size() < (8 << 20) or t.is_pinned() or not t.is_contiguous():
+        return t.cuda(non_blocking=t.is_pinned())
+    from . import staging
+    return staging.upload(t)
 
 
 def as_host_records(records, batch=None):
@@ -109,7 +134,7 @@ def render_records(svbrdf, records):
     rec = as_host_records(records, maps.shape[0])
     images = _RenderRecords.apply(maps, rec)
     images = images.reshape(lead + tuple(images.shape[1:]))
-    return images if origin.type == "cuda" else images.to(origin)
+    return origin.restore(images)
 
 
 class LocalRenderer:
@@ -127,4 +152,30 @@ class LocalRenderer:
         return images.unsqueeze(0) if images.dim() == 3 else images
 
 
-__all__ = ["LocalRenderer", "render_records", "coordinate_table"]
+_PATH_TRACER = None
+
+
+def register_path_tracer(cls):
+    """Makes ``RednerRenderer()`` construct ``cls`` - e.g. the reference's own ``renderers.RednerRenderer`` imported
+    from its module under another name before ``sys.modules['renderers']`` is swapped."""
+    global _PATH_TRACER
+    _PATH_TRACER = cls
+    return cls
+
+
+class RednerRenderer:
+    """Name kept so that ``from renderers import LocalRenderer, RednerRenderer`` (main.py:12) works against this
+    module.  The Redner path tracer (renderers.py:175-270, external ``pyredner``) is outside this library's scope:
+    constructing it returns the class given to :func:`register_path_tracer`, or raises with a pointer to the
+    reference's module.  Any such renderer plugs into ``RenderingLoss`` through the generic per-scene loop."""
+
+    def __new__(cls, *args, **kwargs):
+        if _PATH_TRACER is None:
+            raise NotImplementedError(
+                "RednerRenderer is not part of svbrdf_estimation_b200 (only the in-network renderer is): import the "
+                "reference's development/multiImage_pytorch/renderers.py (needs pyredner) and either use its "
+                "RednerRenderer directly or pass it to svbrdf_estimation_b200.renderers.register_path_tracer()")
+        return _PATH_TRACER(*args, **kwargs)
+
+
+__all__ = ["LocalRenderer", "RednerRenderer", "register_path_tracer", "render_records", "coordinate_table"]

@@ -1,0 +1,52 @@
+"""Host -> device staging for callers that hand pageable CPU tensors to the loss / renderer.
+
+``tensor.cuda()`` on pageable memory is a blocking copy through the driver's own small bounce buffer.  Here the
+tensor is cut into chunks that are copied by the CPU (torch's multi-threaded ``copy_``) into one of two pinned
+buffers and sent with ``cudaMemcpyAsync`` on the current stream, so the CPU copy of chunk ``i+1`` overlaps the DMA
+of chunk ``i`` and the transfer runs at min(host memcpy, PCIe) instead of their sum.  Stream-ordered: kernels
+enqueued afterwards on the current stream see the data; the host returns when the last chunk has been *enqueued*.
+"""
+import threading
+
+import torch
+
+CHUNK_BYTES = 32 << 20
+_lock = threading.Lock()
+_state = {}     # device index -> (pinned buffers, events)
+
+
+def _buffers(index):
+    st = _state.get(index)
+    if st is None:
+        bufs = [torch.empty(CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+        st = _state[index] = (bufs, evs)
+    return st
+
+
+def upload(t, device=None):
+    """Contiguous CPU tensor -> new CUDA tensor with the same shape and dtype on ``device`` (default: current)."""
+    if t.is_cuda:
+        return t
+    if not t.is_contiguous():
+        t = t.contiguous()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return out
+    src = t.detach().view(-1).view(torch.uint8)
+    dst = out.view(-1).view(torch.uint8)
+    with _lock, torch.cuda.device(device):
+        bufs, evs = _buffers(device.index)
+        for i, lo in enumerate(range(0, nbytes, CHUNK_BYTES)):
+            n = min(CHUNK_BYTES, nbytes - lo)
+            k = i & 1
+            evs[k].synchronize()                               # the DMA that last read this pinned buffer is done
+            bufs[k][:n].copy_(src[lo:lo + n])                  # CPU copy into pinned memory (overlaps the previous DMA)
+            dst[lo:lo + n].copy_(bufs[k][:n], non_blocking=True)
+            evs[k].record()
+    return out
+
+
+__all__ = ["upload", "CHUNK_BYTES"]

@@ -125,9 +125,17 @@ def main():
     ref_env, ref_losses, ref_renderers, ref_utils = ref
 
     # 1. sampler pins -------------------------------------------------------------------
-    np.savez(os.path.join(HERE, "scenes.npz"),
-             seed313_b4_r3_s6=sample_configs(ref_env, 313, 4, 3, 6).numpy(),
-             seed7_b2_r9_s18=sample_configs(ref_env, 7, 2, 9, 18).numpy())
+    scenes = dict(seed313_b4_r3_s6=sample_configs(ref_env, 313, 4, 3, 6).numpy(),
+                  seed7_b2_r9_s18=sample_configs(ref_env, 7, 2, 9, 18).numpy())
+    # more shapes (odd counts leave a cached Box-Muller sample in the generator; 0 random / 0 specular), each followed by
+    # four draws from the global generator: pins the generator state the reference leaves behind
+    for seed, batch, nr, ns in ((1, 3, 3, 6), (2, 5, 2, 3), (3, 4, 1, 5), (4, 2, 0, 7), (5, 3, 4, 0), (6, 2, 9, 15), (11, 16, 3, 6)):
+        key = "seed%d_b%d_r%d_s%d" % (seed, batch, nr, ns)
+        scenes[key] = sample_configs(ref_env, seed, batch, nr, ns).numpy()
+        scenes[key + "_next"] = torch.rand(4).numpy()
+    np.savez(os.path.join(HERE, "scenes.npz"), **scenes)
+    if "--only-scenes" in sys.argv:
+        return
     torch.manual_seed(99)
     dirs = ref_utils.generate_normalized_random_direction(5, 0.001, 0.1).numpy()
     np.savez(os.path.join(HERE, "directions.npz"), seed99_count5=dirs)

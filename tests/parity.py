@@ -104,3 +104,93 @@ def clamp_ambiguous_pixels(maps, cfg, rel=2e-3):
         amb = amb | near(q, 1e-3)
     amb = amb.any(1) | near(m[:, 6:9], 1e-3).any(1)
     return amb[:, None].numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Term-level treatment of the sign of an L1 term
+# ---------------------------------------------------------------------------------------------------------------------
+def flipped_term_analysis(O, inp, tgt, cfg, g_ours, scale=1.0, device=None, thr=AMBIGUOUS_DLOG, max_slots=6):
+    """Which individual L1 terms did an fp32 evaluation take with the other sign than the fp64 oracle?
+
+    The loss is ``mean |l|`` with ``l = log(R_in + 0.1) - log(R_tgt + 0.1)`` per (element, record, colour, pixel)
+    (losses.py:46-50), so each term contributes ``sign(l) * J`` to the gradient of its pixel, ``J`` its Jacobian w.r.t. the
+    pixel's 12 map values.  A term whose fp64 value is 0 < |l| < ``thr`` can come out with either sign in fp32 (the
+    reference's own fp32 run included); everything else cannot.  For every such CANDIDATE term the oracle's Jacobian is
+    computed in fp64 (one autograd pass per candidate rank within a pixel), and per pixel the subset of candidates whose
+    flip (``-2 sign(l) J``) best explains ``g_ours - g64`` is taken as flipped.  Nothing else is removed or masked.
+
+    ``inp`` / ``tgt`` [B,12,H,W] and ``cfg`` [B,N,9] are the oracle's problem, ``g_ours`` the fp32 gradient for the same
+    elements times ``scale`` (= B_full / B when the kernel ran on a larger batch than the oracle's subset).
+    Returns a dict: ``g64``, ``loss64``, ``g_corrected`` (= g_ours with the flipped terms put back to the fp64 sign),
+    ``candidates``, ``flipped``, ``max_abs_l_flipped``, ``pixels_over_slots``."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    x64 = torch.as_tensor(inp).double().to(dev)
+    t64 = torch.as_tensor(tgt).double().to(dev)
+    cfg = torch.as_tensor(cfg)
+    B, _, H, W = x64.shape
+    N = cfg.shape[1]
+    M = float(B * N * 3 * H * W)
+    loss64, g64 = O.rendering_loss_and_grad(x64, t64, cfg)
+    with torch.no_grad():
+        l = torch.log(O.render_batch(x64, cfg) + 0.1) - torch.log(O.render_batch(t64, cfg) + 0.1)      # [B,N,3,H,W]
+        amb = ((l != 0) & (l.abs() < thr)).flatten(1, 2)                                                 # [B,3N,H,W]
+        rank = amb.cumsum(1) * amb                                                                       # 1-based rank of a candidate in its pixel
+        per_pixel = amb.sum(1)                                                                           # [B,H,W]
+        slots = int(min(int(per_pixel.max()), max_slots))
+        sign = torch.sign(l).flatten(1, 2)
+    contrib, labs = [], []
+    for j in range(1, slots + 1):
+        sel = (rank == j)
+        xs = x64.clone().requires_grad_(True)
+        r = O.render_batch(xs, cfg)
+        (sel.view_as(l).double() * torch.log(r + 0.1)).sum().backward()
+        with torch.no_grad():
+            s_j = (sel * sign).sum(1)                                                                    # [B,H,W], 0 where the pixel has no j-th candidate
+            contrib.append(xs.grad / M * s_j[:, None])                                                   # the term's share of g64
+            labs.append((sel * l.flatten(1, 2).abs()).sum(1))
+    with torch.no_grad():
+        g_ours = torch.as_tensor(g_ours).double().to(dev) * float(scale)
+        resid = g_ours - g64
+        best_err = (resid ** 2).sum(1)                                                                   # no flip
+        best_mask = torch.zeros_like(best_err, dtype=torch.long)
+        for m in range(1, 1 << slots):
+            corr = sum(contrib[j] for j in range(slots) if (m >> j) & 1)
+            valid = torch.ones_like(best_err, dtype=torch.bool)
+            for j in range(slots):
+                if (m >> j) & 1:
+                    valid &= per_pixel > j
+            err = ((resid + 2.0 * corr) ** 2).sum(1)
+            take = valid & (err < best_err)
+            best_err = torch.where(take, err, best_err)
+            best_mask = torch.where(take, torch.full_like(best_mask, m), best_mask)
+        g_corr = g_ours.clone()
+        flipped, max_l = 0, 0.0
+        for j in range(slots):
+            on = ((best_mask >> j) & 1).bool()
+            g_corr = g_corr + 2.0 * contrib[j] * on[:, None]
+            flipped += int(on.sum())
+            if on.any():
+                max_l = max(max_l, float(labs[j][on].max()))
+    return {"g64": g64.cpu().numpy(), "loss64": float(loss64), "g_corrected": g_corr.cpu().numpy(), "g_ours": g_ours.cpu().numpy(),
+            "candidates": int(amb.sum()), "flipped": flipped, "max_abs_l_flipped": max_l, "terms": int(B * N * 3 * H * W),
+            "pixels_over_slots": int((per_pixel > slots).sum())}
+
+
+def check_grad_with_flipped_terms(res, name, rel=REL_L2, thr=AMBIGUOUS_DLOG):
+    """Asserts on a :func:`flipped_term_analysis` result: every flipped term is sign-ambiguous in fp64 (|l| < thr), they
+    are a vanishing share of all terms, and with ONLY those terms put back the gradient is within ``rel`` rel-L2 of the
+    fp64 oracle in every map group over ALL pixels (nothing masked); with no flipped term the raw gradient already is."""
+    assert res["pixels_over_slots"] == 0, "%s: pixels with more candidate terms than analysed" % name
+    assert res["flipped"] <= res["candidates"]
+    # an fp32 evaluation flips a candidate only when its own error in l (~1e-5) exceeds |l|: a few percent of them
+    assert res["flipped"] <= 0.05 * res["candidates"] + 2, "%s: %d flipped terms of %d candidates" % (name, res["flipped"], res["candidates"])
+    assert res["max_abs_l_flipped"] < thr, "%s: a flipped term has |l| = %.3g in fp64" % (name, res["max_abs_l_flipped"])
+    out = {}
+    for g, s in GROUPS:
+        e = rel_l2(res["g_corrected"][:, s], res["g64"][:, s])
+        out[g] = {"corrected": e, "raw": rel_l2(res["g_ours"][:, s], res["g64"][:, s])}
+        assert e <= rel, "%s[%s]: rel-L2 %.3g after putting back %d flipped term(s)" % (name, g, e, res["flipped"])
+        if res["flipped"] == 0:
+            assert out[g]["raw"] <= rel, "%s[%s]: rel-L2 %.3g with no flipped term" % (name, g, out[g]["raw"])
+    return out

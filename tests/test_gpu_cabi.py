@@ -82,7 +82,9 @@ def test_forward_only_forward_backward_and_mixed_agree(env):
 
 
 def test_unaligned_pointers_and_odd_width_take_the_scalar_kernels(env):
-    """W odd -> one pixel per thread kernels; result equals the packed kernels' on an even-width crop."""
+    """Odd W, or an even W whose planes start at an odd float offset (a contiguous view into a larger buffer: 4-byte but
+    not 8-byte aligned), run the one-pixel-per-thread kernels; the result equals the packed kernels' to rounding and the
+    oracle's within the parity tolerance.  Pointers that are not even float-aligned are rejected."""
     lib, _cabi, E = env
     import svbrdf_estimation_b200 as S
     from oracle import reference_port as O
@@ -95,6 +97,43 @@ def test_unaligned_pointers_and_odd_width_take_the_scalar_kernels(env):
     loss.backward()
     assert abs(float(loss) - float(l64)) <= 2e-6 * float(l64)
     assert float((x.grad.cpu().double() - g64).norm() / g64.norm()) <= 1e-4
+    # even width, every tensor shifted by one float inside a larger allocation
+    B, size = 2, 32
+    inp, tgt = synthetic_maps(B, size, 7), synthetic_maps(B, size, 8)
+    n = inp.numel()
+
+    def shifted(t):
+        buf = torch.empty(t.numel() + 1, device="cuda")
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 8 == 4 and v.is_contiguous()
+        return v
+    a, b = shifted(inp), shifted(tgt)
+    o_al, g_al = device_loss(lib, _cabi, inp.cuda(), tgt.cuda(), rec)
+    gbuf = torch.empty(n + 1, device="cuda")
+    g_un = gbuf[1:].view(inp.shape)
+    lin = shifted(torch.linspace(-1, 1, size))
+    nbytes = lib.svbrdf_b200_workspace_bytes(B, 9, size, size)
+    ws = torch.empty(nbytes // 4 + 1, device="cuda")
+    out = torch.zeros(3, device="cuda")
+    _cabi.check(lib.svbrdf_b200_loss_forward_backward(a.data_ptr(), b.data_ptr(), B, size, size, rec.data_ptr(), 9, lin.data_ptr(),
+                                                      out.data_ptr(), g_un.data_ptr(), ws.data_ptr(), nbytes, None))
+    torch.cuda.synchronize()
+    assert abs(float(out[0]) - float(o_al[0])) <= 1e-6 * float(o_al[0])
+    torch.testing.assert_close(g_un, g_al, rtol=2e-4, atol=1e-9)          # scalar vs packed lanes: different instruction streams
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), rec)
+    assert float((g_un.cpu().double() - g64).norm() / g64.norm()) <= 1e-4
+    # renderer: unaligned maps and images
+    img_al = S.render_records(inp.cuda(), rec)
+    imgbuf = torch.empty(B * 9 * 3 * size * size + 1, device="cuda")
+    img_un = imgbuf[1:].view(B, 9, 3, size, size)
+    _cabi.check(lib.svbrdf_b200_render_forward(a.data_ptr(), B, size, size, rec.data_ptr(), 9, 1, lin.data_ptr(), img_un.data_ptr(), None))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(img_un, img_al, rtol=1e-5, atol=1e-7)
+    # a pointer that is not float-aligned is an error
+    st = lib.svbrdf_b200_loss_forward(a.data_ptr() + 1, b.data_ptr(), B, size, size, rec.data_ptr(), 9, lin.data_ptr(),
+                                      out.data_ptr(), ws.data_ptr(), nbytes, None)
+    assert st == _cabi.E_INVALID and b"aligned" in lib.svbrdf_b200_last_error()
 
 
 @pytest.mark.parametrize("workload", ["c2", "c4"])
@@ -213,4 +252,4 @@ def test_plain_c_program_through_the_host_entry(env, tmp_path):
     from oracle import reference_port as O                      # and both agree with the reference's math
     l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), rec)
     assert abs(c_loss - float(l64)) <= 2e-6 * float(l64)
-    assert float((c_grad.double() - g64).norm() / g64.norm()) <= 1.5e-4
+    assert float((c_grad.double() - g64).norm() / g64.norm()) <= 1e-4

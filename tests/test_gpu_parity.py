@@ -82,9 +82,15 @@ def test_mixed_loss_vs_reference(S, golden):
     assert val.dim() == 0
     assert abs(float(val) - float(gm["loss_f32"])) <= 3e-6 * abs(float(gm["loss_f32"]))
     o32 = gm["grad_f32"]
+    torch.manual_seed(int(gm["seed"]))
+    cfg = O.sample_loss_configs(g["input"].shape[0])
+    x64 = torch.from_numpy(g["input"]).double().requires_grad_(True)
+    O.mixed_loss(x64, torch.from_numpy(g["target"]).double(), cfg, 0.1).backward()
     for name, s in parity.GROUPS:
-        e = parity.rel_l2(x.grad.cpu().numpy()[:, s], o32[:, s])
-        assert e <= 1.5e-4, (name, e)
+        got = x.grad.cpu().numpy()[:, s]
+        assert parity.rel_l2(got, x64.grad.numpy()[:, s]) <= parity.REL_L2, name          # vs the fp64 oracle: 1e-4
+        floor = parity.rel_l2(o32[:, s], x64.grad.numpy()[:, s])                          # the reference's own fp32 run
+        assert parity.rel_l2(got, o32[:, s]) <= max(parity.REL_L2, 2 * floor), name
     # unfused SVBRDFL1Loss on the device
     l1 = S.SVBRDFL1Loss()(cu(g["input"]), cu(g["target"]))
     assert abs(float(l1) - float(gm["l1_f32"])) <= 1e-5 * float(gm["l1_f32"])
@@ -219,7 +225,7 @@ def test_argument_errors(S):
     with pytest.raises(ValueError):
         r.render(scene, torch.zeros(11, 8, 8).cuda())
     with pytest.raises(TypeError):
-        r.render(scene, torch.zeros(12, 8, 8, dtype=torch.float64).cuda())
+        r.render(scene, torch.zeros(12, 8, 8, dtype=torch.int32).cuda())
     with pytest.raises(ValueError):
         S.rendering_loss_with_records(torch.zeros(2, 12, 8, 8).cuda(), torch.zeros(1, 12, 8, 8).cuda(), torch.zeros(2, 9, 9))
     with pytest.raises(ValueError):
@@ -304,7 +310,7 @@ def test_encoded_input_mixed_loss(S, golden):
     assert abs(float(out[0]) - float(want)) <= 3e-6 * float(want)
     g64 = e64.grad.numpy()
     for name, s in (("normal_xy", slice(0, 2)), ("diffuse", slice(2, 5)), ("roughness", slice(5, 6)), ("specular", slice(6, 9))):
-        assert parity.rel_l2(x.grad.cpu().numpy()[:, s], g64[:, s]) <= 1.5e-4, name
+        assert parity.rel_l2(x.grad.cpu().numpy()[:, s], g64[:, s]) <= parity.REL_L2, name
     # module form draws the reference's scenes and equals the decoded 12-channel path
     torch.manual_seed(9)
     a = S.MixedLoss(S.LocalRenderer()).forward_encoded(enc.cuda(), tgt.cuda())
@@ -416,27 +422,97 @@ def test_dataset_input_synthesis_matches_reference(S, golden):
     assert fast.shape == (4, 3, 16, 16) and float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0
 
 
-@pytest.mark.parametrize("shape", [(4, 256, 3, 6), (2, 256, 9, 18)])
-def test_full_resolution_gradient_parity(S, shape):
-    """BASELINE.json shapes at full resolution (256x256, N = 9 and N = 27): the oracle runs on the GPU in fp64 for the
-    ground truth.  Gradients are compared over the pixels without a sign-ambiguous L1 term (tests/parity.py)."""
-    batch, size, nr, ns = shape
+def _oracle_loss_chunks(inp, tgt, cfg, dev, chunk):
+    """fp64 oracle loss of a large batch, evaluated forward-only in chunks on the GPU (equal chunk sizes)."""
+    B = inp.shape[0]
+    assert B % chunk == 0
+    with torch.no_grad():
+        vals = [float(O.rendering_loss(inp[i:i + chunk].double().to(dev), tgt[i:i + chunk].double().to(dev), cfg[i:i + chunk]))
+                for i in range(0, B, chunk)]
+    return sum(vals) / len(vals)
+
+
+# (name, batch, size, n_random, n_specular, batch elements the fp64 oracle differentiates, forward chunk)
+FULL_SIZE_CASES = [
+    ("c1_b8_256_n9", 8, 256, 3, 6, 8, 8),            # BASELINE.json configs[0] at its real batch
+    ("c2_b64_256_n9", 64, 256, 3, 6, 8, 8),          # configs[1]: the kernel runs all 64 maps, the oracle every 8th
+    ("c3_b32_256_n27", 32, 256, 9, 18, 4, 4),        # configs[2]
+    ("c4_b16_1024_n9", 16, 1024, 3, 6, 1, 1),        # configs[3]: renderers.py:73-76 coordinates at W = 1024
+    ("c5_b32_256_n9", 32, 256, 3, 6, 8, 8),          # configs[4], one rank's slice
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE_CASES, ids=[c[0] for c in FULL_SIZE_CASES])
+def test_full_resolution_parity_at_the_baseline_configs(S, case):
+    """BASELINE.json configs at full size (losses.py:34-50, renderers.py:73-76): the CUDA path runs the whole batch;
+    the oracle runs on the GPU in fp64 - the loss over the whole batch (forward only, in chunks), the gradient for a
+    strided subset of the batch elements.  Gradients are compared over ALL pixels: the only thing set aside are the
+    individual L1 terms the fp32 evaluation took with the other sign, each of which must be sign-ambiguous in fp64
+    (0 < |l| < 1e-3) - tests/parity.py flipped_term_analysis."""
+    name, batch, size, nr, ns, n_sub, chunk = case
     dev = torch.device("cuda", 0)
     inp, tgt = synthetic_maps(batch, size, 21), synthetic_maps(batch, size, 22)
     torch.manual_seed(313)
     cfg = O.sample_loss_configs(batch, nr, ns)
-    l64, g64 = O.rendering_loss_and_grad(inp.double().to(dev), tgt.double().to(dev), cfg)
-    with torch.no_grad():
-        keep = parity.unambiguous_pixels(O.render_batch(inp.double().to(dev), cfg).cpu().numpy(),
-                                         O.render_batch(tgt.double().to(dev), cfg).cpu().numpy())
     x = inp.to(dev).requires_grad_(True)
     loss = S.rendering_loss_with_records(x, tgt.to(dev), cfg)
     loss.backward()
-    parity.check_loss(float(loss), float(l64))
-    assert keep.mean() >= 0.9, "too many sign-ambiguous pixels: %.3f" % (1 - keep.mean())
-    g, g64 = x.grad.cpu().numpy(), g64.cpu().numpy()
-    for name, s in parity.GROUPS:
-        assert parity.rel_l2(g[:, s] * keep, g64[:, s] * keep) <= parity.REL_L2, name
+    parity.check_loss(float(loss), _oracle_loss_chunks(inp, tgt, cfg, dev, chunk))
+    sub = list(range(0, batch, batch // n_sub))[:n_sub]
+    g = x.grad[sub].cpu().numpy()
+    res = parity.flipped_term_analysis(O, inp[sub], tgt[sub], cfg[sub], g, scale=batch / float(len(sub)), device=dev)
+    out = parity.check_grad_with_flipped_terms(res, name)
+    print(name, "candidates %d flipped %d max|l| %.2e" % (res["candidates"], res["flipped"], res["max_abs_l_flipped"]), out)
+
+
+def test_interface_second_backward_eval_mode_and_dtype_following(S):
+    """retain_graph=True allows a second backward (the reference's eager graph does); an .eval()-mode loss computes no
+    gradient up front but backward() still works; float64 maps give float64 results (renderers.py:68: dtype follows)."""
+    inp, tgt = synthetic_maps(2, 32, 5).cuda(), synthetic_maps(2, 32, 6).cuda()
+    cfg = O.sample_loss_configs(2)
+    x = inp.clone().requires_grad_(True)
+    loss = S.rendering_loss_with_records(x, tgt, cfg)
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone()
+    loss.backward()                                           # second time: gradient recomputed, accumulated
+    torch.testing.assert_close(x.grad, 2 * g1, rtol=1e-6, atol=0)
+    with pytest.raises(RuntimeError):
+        loss.backward()                                       # graph freed now, like any autograd graph
+    with pytest.raises(RuntimeError):                         # once differentiable: no silent zero second derivative
+        y = inp.clone().requires_grad_(True)
+        torch.autograd.grad(S.rendering_loss_with_records(y, tgt, cfg), y, create_graph=True)[0].sum().backward()
+    # validation mode (main.py:140 evaluates the loss without no_grad): no gradient pass, same value, lazy backward
+    mod = S.MixedLoss(S.LocalRenderer()).eval()
+    x2 = inp.clone().requires_grad_(True)
+    torch.manual_seed(4)
+    v = mod(x2, tgt)
+    torch.manual_seed(4)
+    x3 = inp.clone().requires_grad_(True)
+    w = S.MixedLoss(S.LocalRenderer())(x3, tgt)
+    assert abs(float(v) - float(w)) <= 1e-6 * float(w)
+    v.backward(); w.backward()
+    torch.testing.assert_close(x2.grad, x3.grad, rtol=0, atol=0)
+    # dtype following
+    r = S.LocalRenderer()
+    scene = S.Scene(S.Camera([0.0, -1.0, 2.0]), S.Light([0.0, 0.0, 2.0], [50.0, 50.0, 50.0]))
+    img64 = r.render(scene, inp.double())
+    assert img64.dtype == torch.float64
+    torch.testing.assert_close(img64, r.render(scene, inp).double(), rtol=0, atol=0)
+    x64 = inp.double().requires_grad_(True)
+    l64 = S.rendering_loss_with_records(x64, tgt.double(), cfg)
+    l64.backward()
+    assert l64.dtype == torch.float64 and x64.grad.dtype == torch.float64
+    torch.testing.assert_close(x64.grad, g1.double(), rtol=1e-6, atol=0)
+    # accurate-highlight kernels without a gradient: the forward-only kernel (no scratch gradient buffer)
+    with torch.no_grad():
+        va = S.rendering_loss_with_records(inp, tgt, cfg, accurate=True)
+    xa = inp.clone().requires_grad_(True)
+    vb = S.rendering_loss_with_records(xa, tgt, cfg, accurate=True)
+    assert abs(float(va) - float(vb)) <= 1e-6 * float(vb)
+    # encoded input on another device than the target is an error, not a cross-device launch
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(ValueError):
+            S.mixed_loss_from_encoded(torch.zeros(2, 9, 32, 32, device="cuda:1"), tgt, cfg)
 
 
 def test_random_shapes_against_the_oracle_on_gpu(S):

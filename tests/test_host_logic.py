@@ -29,7 +29,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
         assert n in _cabi.PROTOTYPES, "no ctypes prototype for " + n
     assert set(_cabi.PROTOTYPES) == set(names)
-    assert lib.svbrdf_b200_abi_version() == 1
+    assert lib.svbrdf_b200_abi_version() == _cabi.ABI_VERSION == 2
+    from svbrdf_estimation_b200 import _build
+    assert lib.svbrdf_b200_build_id().decode() == _build.ID_MARKER + _build.source_id()      # the binary is built from these sources
+    assert not any('probe' in n for n in names)                                               # measurement helpers are not product ABI
     # pure host-side entry points work without a GPU
     assert lib.svbrdf_b200_workspace_bytes(64, 9, 256, 256) >= 64 * 256 * 4 * 2
     assert lib.svbrdf_b200_workspace_bytes(0, 0, 0, 0) > 0
@@ -89,6 +92,39 @@ def test_samplers_match_reference_draw_order(golden):
     torch.manual_seed(99)
     np.testing.assert_array_equal(E.generate_normalized_random_direction(5, 0.001, 0.1).numpy(),
                                   golden("directions")["seed99_count5"])
+
+
+def test_native_reference_order_sampler_is_bit_identical(golden):
+    """csrc/scene_sampler.cpp restates ATen's mt19937 / uniform_ / normal_ (scalar path with its cached Box-Muller sample)
+    and the samplers' float arithmetic: same scenes as the unmodified reference (fixtures), same scenes AND same
+    generator state as the torch-call path for every shape, including a pending cached normal sample."""
+    from svbrdf_estimation_b200 import environment as E
+    g = golden("scenes")
+    for key in sorted(k for k in g if k.endswith("_next")):
+        seed, batch, nr, ns = (int(t[1:]) if i else int(t[4:]) for i, t in enumerate(key[:-5].split("_")))
+        for native in (True, False):
+            torch.manual_seed(seed)
+            got = E.sample_loss_configs(batch, nr, ns, native_draws=native)
+            np.testing.assert_array_equal(got.numpy(), g[key[:-5]], err_msg="%s native=%s" % (key, native))
+            np.testing.assert_array_equal(torch.rand(4).numpy(), g[key], err_msg="generator state after %s native=%s" % (key, native))
+    for seed in range(40):
+        for batch, nr, ns in ((5, 3, 6), (3, 2, 3), (2, 0, 7), (4, 3, 0), (33, 3, 6)):
+            torch.manual_seed(seed)
+            if seed % 3 == 1:
+                torch.empty(1, dtype=torch.float64).normal_()        # leaves a cached double sample behind
+            s0 = torch.get_rng_state()
+            a = E.sample_loss_configs(batch, nr, ns, native_draws=False)
+            sa = torch.get_rng_state()
+            torch.set_rng_state(s0)
+            b = E.sample_loss_configs(batch, nr, ns)
+            assert torch.equal(a, b) and torch.equal(sa, torch.get_rng_state()), (seed, batch, nr, ns)
+    # n_specular >= 16: normal_() takes ATen's vectorised path - the native draws refuse, the sampler goes through torch
+    from svbrdf_estimation_b200 import _cabi
+    st = torch.get_rng_state()
+    buf = torch.empty(4096)
+    rc = _cabi.lib().svbrdf_b200_reference_draws(st.data_ptr(), st.numel(), 1, 1, 16, buf.data_ptr(), buf.data_ptr())
+    assert rc == _cabi.E_INVALID
+    assert _cabi.lib().svbrdf_b200_reference_draws(st.data_ptr(), 100, 1, 3, 6, buf.data_ptr(), buf.data_ptr()) == _cabi.E_STATE
 
 
 def test_fast_sampler_distribution():
@@ -248,3 +284,47 @@ def test_bench_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "c1" and d["n_gpus"] == 1 and d["steps"] == 1
+
+
+def test_reference_import_lines_work_against_the_swapped_modules():
+    """INTEGRATION.md section 1, the no-touch swap: main.py:8,12 and dataset.py:1,7 import statements executed verbatim
+    against sys.modules entries pointing at this package, then the loss is built as main.py:82-89 does."""
+    import svbrdf_estimation_b200 as b200
+    names = ("losses", "renderers", "environment")
+    saved = {n: sys.modules.get(n) for n in names}
+    try:
+        sys.modules["losses"], sys.modules["renderers"], sys.modules["environment"] = b200.losses, b200.renderers, b200.environment
+        ns = {}
+        exec("from losses import MixedLoss\n"                                  # main.py:8
+             "from renderers import LocalRenderer, RednerRenderer\n"           # main.py:12
+             "import environment as env\n"                                     # dataset.py:1, losses.py:1
+             "import renderers\n", ns)                                         # dataset.py:7, losses.py:2
+        loss_renderer = ns["LocalRenderer"]()                                  # main.py:84
+        loss_function = ns["MixedLoss"](loss_renderer)                         # main.py:89
+        assert loss_function.l1_weight == 0.1 and loss_function.rendering_loss.renderer is loss_renderer
+        assert loss_function.rendering_loss.random_configuration_count == 3
+        assert loss_function.rendering_loss.specular_configuration_count == 6
+        assert isinstance(ns["renderers"].LocalRenderer(), b200.LocalRenderer)  # dataset.py:206
+        scene = ns["env"].Scene(ns["env"].Camera([0.0, 0.0, 1.0]), ns["env"].Light([0.0, 0.0, 1.0], [1.0, 1.0, 1.0]))   # dataset.py:210
+        assert scene.light.color == [1.0, 1.0, 1.0]
+        # --renderer pathtracing (main.py:85-86): the name imports; constructing it points at the reference's module ...
+        with pytest.raises(NotImplementedError, match="pyredner"):
+            ns["RednerRenderer"]()
+
+        class FakePathTracer:                                                  # ... or builds what was registered
+            def __init__(self, use_gpu=True):
+                self.use_gpu = use_gpu
+
+            def render(self, scene, svbrdf):
+                raise AssertionError("not called here")
+        b200.renderers.register_path_tracer(FakePathTracer)
+        pt = ns["RednerRenderer"](use_gpu=False)
+        assert isinstance(pt, FakePathTracer) and pt.use_gpu is False
+        assert not getattr(ns["MixedLoss"](pt).rendering_loss.renderer, "fused_rendering_loss", False)
+    finally:
+        b200.renderers.register_path_tracer(None)
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m

@@ -168,3 +168,59 @@ def test_accurate_loss_is_closer_to_fp64_than_the_reference_fp32_run(golden, lan
         e64 = parity.rel_l2(grad[:, s], g["grad_f64"][:, s])
         floor = parity.rel_l2(g["grad_f32"][:, s], g["grad_f64"][:, s])
         assert e64 <= max(0.3 * floor, 3e-7), (name, e64, floor)
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_maps_that_differ_bitwise_but_render_identically_are_exact_zeros(lanes):
+    """Two roughness values below the clamp of renderers.py:87 are the same material, and the diffuse albedo does not
+    matter where the specular albedo is exactly 1 ((1-F) d = 0, renderers.py:18-20,32): the reference renders such pairs
+    bit-identically and their terms contribute exactly 0 (sign(0) = 0, losses.py:50).  The kernels decide identity on the
+    parameters the shading consumes, so they do too - instead of handing a full-magnitude +-1/x gradient to rounding noise."""
+    from tests.common import synthetic_maps
+    tgt = synthetic_maps(2, 16, 3)
+    inp = tgt.clone()
+    inp[0, 6:9] = 2e-4                      # element 0: roughness below the clamp on both maps, different bits
+    tgt[0, 6:9] = 7e-4
+    inp[1, 9:12] = 1.0                      # element 1: specular albedo exactly 1 on both maps, different diffuse albedo
+    tgt[1, 9:12] = 1.0
+    inp[1, 3:6] = torch.rand(3, 16, 16)
+    torch.manual_seed(2)
+    cfg = O.sample_loss_configs(2)
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+    assert float(l64) == 0.0 and not bool(g64.any())                     # the reference: exactly zero
+    loss, grad = emu.loss_forward_backward(inp.numpy(), tgt.numpy(), cfg.numpy(), lanes)
+    assert loss == 0.0 and not grad.any()
+    # a mixed case: only colour channel 1 of element 1 really differs (its specular albedo moves off 1)
+    inp[1, 10] = 0.5
+    l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), cfg)
+    loss, grad = emu.loss_forward_backward(inp.numpy(), tgt.numpy(), cfg.numpy(), lanes)
+    parity.check_loss(loss, float(l64))
+    assert not grad[0].any() and not grad[1, [3, 5, 6, 8, 9, 11]].any()
+    assert parity.rel_l2(grad, g64.numpy()) <= 1e-4
+
+
+def test_flipped_term_analysis_recovers_planted_flips():
+    """tests/parity.py flipped_term_analysis: plant sign flips on a few sign-ambiguous L1 terms of the fp64 gradient (and on
+    no other term) and check that exactly those are found and put back."""
+    from tests.common import synthetic_maps
+    inp, tgt = synthetic_maps(2, 48, 21), synthetic_maps(2, 48, 22)
+    torch.manual_seed(313)
+    cfg = O.sample_loss_configs(2)
+    x = inp.double().requires_grad_(True)
+    l = torch.log(O.render_batch(x, cfg) + 0.1) - torch.log(O.render_batch(tgt.double(), cfg) + 0.1)
+    amb = ((l != 0) & (l.abs() < parity.AMBIGUOUS_DLOG)).detach()
+    idx = amb.nonzero()
+    assert len(idx) >= 6
+    planted = idx[:: max(1, len(idx) // 5)][:5]
+    sign = torch.sign(l.detach())
+    for i in planted:
+        sign[tuple(i)] *= -1.0
+    (sign * l).mean().backward()                                        # gradient of the loss with those terms flipped
+    res = parity.flipped_term_analysis(O, inp, tgt, cfg, x.grad.numpy())
+    assert res["flipped"] == len(planted) and res["candidates"] == int(amb.sum())
+    assert 0 < res["max_abs_l_flipped"] < parity.AMBIGUOUS_DLOG
+    out = parity.check_grad_with_flipped_terms(res, "planted", rel=1e-10)
+    assert max(v["raw"] for v in out.values()) > 1e-6                   # the flips were visible before the correction
+    # the unmodified fp64 gradient has no flipped term
+    res0 = parity.flipped_term_analysis(O, inp, tgt, cfg, res["g64"])
+    assert res0["flipped"] == 0
