@@ -147,37 +147,51 @@ def cpu_port_step(inp, tgt, cfg):
     return O.rendering_loss_and_grad(inp, tgt, cfg)
 
 
-def time_cpu_port(workload, steps, warmup, budget_s):
-    """Times the oracle port on a bounded sample (first ``b`` batch elements) of the workload.
-    Returns (G evals/s, seconds per step, sample batch, threads)."""
+def cpu_reference_impl():
+    """-> (step function, kind): the unmodified reference (its bytecode under oracle/_ref, built by oracle/build_ref.py in
+    the build container) when it is there, else the restatement in oracle/reference_port.py."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available() and ref_loader.load() is not None:
+            return ref_loader.rendering_loss_and_grad, "reference"
+    except Exception:
+        pass
+    return cpu_port_step, "port"
+
+
+def time_cpu_port(workload, steps, warmup, budget_s, full_batch=False):
+    """Times the reference's CPU implementation of the path (all host threads) on the workload - the full batch when
+    (steps + warmup) passes fit ``budget_s``, else the largest leading part of the batch that does.
+    Returns (G evals/s, seconds per step, sample batch, threads, kind)."""
     import torch
     from svbrdf_estimation_b200 import environment as E
     B, size, N, nr, ns, _ = WORKLOADS[workload]
+    step_fn, kind = cpu_reference_impl()
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(313)
     probe_b = 1
     inp, tgt = synthetic_maps(probe_b, size, 1001), synthetic_maps(probe_b, size, 2001)
     cfg = E.sample_loss_configs(probe_b, nr, ns)
-    cpu_port_step(inp, tgt, cfg)
+    step_fn(inp, tgt, cfg)
     t0 = time.perf_counter()
-    cpu_port_step(inp, tgt, cfg)
+    step_fn(inp, tgt, cfg)
     t1 = time.perf_counter() - t0
-    b = 8 if size <= 256 else 1
-    while b > 1 and (steps + warmup) * t1 * b > budget_s:
+    b = B if full_batch else (8 if size <= 256 else 1)
+    while b > 1 and (steps + warmup) * t1 * b * 0.8 > budget_s:      # a batch amortises per-call overhead: ~0.8 t1 per element
         b //= 2
-    b = min(b, B)
+    b = max(1, min(b, B))
     inp, tgt = synthetic_maps(b, size, 1001), synthetic_maps(b, size, 2001)
     cfg = E.sample_loss_configs(b, nr, ns)
     for _ in range(warmup):
-        cpu_port_step(inp, tgt, cfg)
+        step_fn(inp, tgt, cfg)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_port_step(inp, tgt, cfg)
+        step_fn(inp, tgt, cfg)
         times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     evals = b * size * size * N
-    return evals / sec / 1e9, sec, b, torch.get_num_threads()
+    return evals / sec / 1e9, sec, b, torch.get_num_threads(), kind
 
 
 def time_gpu_eager_port(workload, dev, batch=2, steps=3):
@@ -206,18 +220,22 @@ def run_reference(args):
         return 0
     B, size, N, nr, ns, desc = WORKLOADS[args.workload]
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    val, sec, b, threads = time_cpu_port(args.workload, steps, warmup, budget_s=150.0)
-    sample = "first %d of %d maps of the workload per step (%dx%d, N=%d), fwd+bwd via autograd" % (b, B, size, size, N)
+    val, sec, b, threads, kind = time_cpu_port(args.workload, steps, warmup, budget_s=240.0, full_batch=True)
+    sample = ("the whole batch of the workload per step" if b == B else "first %d of %d maps of the workload per step" % (b, B)) \
+        + " (%dx%d, N=%d), fwd+bwd via autograd" % (size, size, N)
+    what = ("the UNMODIFIED reference (development/multiImage_pytorch/{losses,renderers,environment,utils}.py compiled to bytecode "
+            "under oracle/_ref by oracle/build_ref.py): RenderingLoss(LocalRenderer()) forward + backward, eager PyTorch on the host cores"
+            if kind == "reference" else
+            "the reference's eager-PyTorch CPU path restated in oracle/reference_port.py (bit-exact to the reference in fp32, "
+            "tests/test_oracle_golden.py); oracle/_ref was not found on this machine")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "batch_per_step": b, "size": size, "N": N},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": args.workload, "description": desc, "batch_per_step": b, "batch_per_gpu": B, "size": size, "N": N,
+                       "same_config_as_gpu_arm": b == B},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "reference = its eager-PyTorch CPU path restated in oracle/reference_port.py (bit-exact to the "
-                    "reference in fp32, tests/test_oracle_golden.py); the reference itself is Python source that does "
-                    "not exist on the GPU box"}
+            "gpu_launches": 0, "note": what}
     args.out.emit(json.dumps(line))
     return 0
 
@@ -253,6 +271,113 @@ def probe_fp32_peaks(lib, torch, stream):
             rate = blocks * 256.0 * iters * ops.value * flop_per_op / (ms * 1e-3) / 1e12
             out[name] = max(out.get(name, 0.0), rate)
     return out
+
+
+def train_step_c5(args, torch, dist, dev, world, rank, local_rank):
+    """BASELINE.json configs[4]: the full single-view training step (main.py:104-118) with the fused MixedLoss, GLOBAL
+    batch 256 sharded over the ranks (strong scaling: 256 / world per GPU), the CNN gradients all-reduced by
+    DistributedDataParallel over NCCL inside the timed region, Adam(lr=1e-5) (main.py:74) included.  The network is
+    examples/unet_standin.py: the reference's generator layer for layer in size and shape (79.99 M parameters -> 320 MB of
+    fp32 gradients per step).  Returns the sub-record for the JSON line (rank 0) - timings are the max over ranks."""
+    import torch.nn as nn
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from unet_standin import UNetStandIn
+    import svbrdf_estimation_b200 as S
+    from svbrdf_estimation_b200 import sharding
+    from svbrdf_estimation_b200.environment import NativeSceneSampler
+    GLOBAL_BATCH, size = args.c5_global_batch, 256
+    lo, hi = sharding.shard_range(GLOBAL_BATCH, rank, world)
+    B = hi - lo
+    torch.manual_seed(313)                                        # same initial weights on every rank
+    torch.backends.cudnn.benchmark = True
+    model = UNetStandIn().to(dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    net = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], bucket_cap_mb=25, gradient_as_bucket_view=True) if world > 1 else model
+    opt = torch.optim.Adam(net.parameters(), lr=1e-5, fused=True)
+    # every rank samples the scenes of ITS batch elements: keyed by the global sample index, so the scenes of the job
+    # do not depend on how the batch is sharded
+    loss_fn = S.MixedLoss(S.LocalRenderer(), l1_weight=0.1, scene_sampler=NativeSceneSampler(seed=313, first_batch_element=lo))
+    g = torch.Generator("cpu").manual_seed(4000)
+    images = torch.rand(GLOBAL_BATCH, 3, 64, 64, generator=g)[lo:hi]
+    images = torch.nn.functional.interpolate(images, size=(size, size), mode="nearest").to(dev).contiguous()
+    target = synthetic_maps(GLOBAL_BATCH if GLOBAL_BATCH <= 32 else 32, size, 5000)
+    target = target.repeat((GLOBAL_BATCH + target.shape[0] - 1) // target.shape[0], 1, 1, 1)[lo:hi].to(dev).contiguous()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(sync=True):
+        import contextlib
+        ctx = contextlib.nullcontext() if (sync or world == 1) else net.no_sync()
+        with ctx:
+            opt.zero_grad(set_to_none=True)
+            enc = net(images)
+            ev[1].record()
+            loss = loss_fn.forward_encoded(enc, target)           # decode + map-L1 + rendering loss + their gradient: ONE kernel
+            ev[2].record()
+            loss.backward()                                       # DDP: bucketed all-reduce overlapped with the U-Net backward
+        opt.step()
+        return loss
+
+    def timed(n, sync=True):
+        barrier()
+        ev[0].record()
+        loss_ms = 0.0
+        for _ in range(n):
+            loss = one_step(sync)
+        ev[3].record()
+        barrier()
+        ms = ev[0].elapsed_time(ev[3]) / n
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), loss
+
+    steps, warm = args.c5_steps, 3
+    for _ in range(warm):
+        one_step()
+    step_ms, loss = timed(steps)
+    one_step()
+    torch.cuda.synchronize()
+    loss_kernel_ms = ev[1].elapsed_time(ev[2])                    # fused MixedLoss forward_encoded (fwd + bwd) of the last step
+    global_loss = float(sharding.global_mean_loss(loss.detach(), B))
+    rec = {"config": "configs[4]: full single-view U-Net training step with the fused rendering loss, global batch %d sharded over %d B200"
+                     % (GLOBAL_BATCH, world),
+           "scaling": "strong", "global_batch": GLOBAL_BATCH, "batch_per_gpu": B, "n_gpus": world, "size": size, "N": 9,
+           "model": "examples/unet_standin.py (shape and size of the reference's SingleViewModel generator)", "params_M": n_params / 1e6,
+           "grad_allreduce_MB": n_params * 4 / 1e6, "dtype": "f32 (cuDNN convolutions with TF32 as torch defaults; loss kernels fp32)",
+           "steps": steps, "step_ms": step_ms, "samples_per_s": GLOBAL_BATCH / (step_ms * 1e-3),
+           "fused_mixed_loss_fwd_bwd_ms": loss_kernel_ms, "loss_share_of_step": loss_kernel_ms / step_ms,
+           "loss_G_evals_per_s_per_gpu": B * size * size * 9 / (loss_kernel_ms * 1e-3) / 1e9, "global_loss": global_loss,
+           "timed_region": "zero_grad + U-Net forward + MixedLoss.forward_encoded + backward (DDP bucketed all-reduce, 25 MB buckets) + fused Adam; CUDA events, max over ranks"}
+    if world > 1:
+        nosync_ms, _ = timed(max(3, steps // 2), sync=False)      # same step without the gradient all-reduce
+        one_step()                                                # leave the replicas consistent again (this one all-reduces)
+        flat = torch.empty(n_params, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dist.all_reduce(flat)
+        e1.record()
+        barrier()
+        ar_ms = e0.elapsed_time(e1) / 5
+        t = torch.tensor([ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+        rec.update({"collective": "NCCL all-reduce (average) of the CNN gradients, %.0f MB, DistributedDataParallel buckets" % (n_params * 4 / 1e6),
+                    "allreduce_alone_ms": ar_ms, "allreduce_bus_GBps": 2.0 * (world - 1) / world * n_params * 4 / (ar_ms * 1e-3) / 1e9,
+                    "step_ms_without_allreduce": nosync_ms, "allreduce_exposed_ms": max(0.0, step_ms - nosync_ms),
+                    "allreduce_overlapped_fraction": max(0.0, min(1.0, 1.0 - (step_ms - nosync_ms) / ar_ms)) if ar_ms > 0 else None})
+        del flat
+    del net, model, opt, images, target
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_ours(args):
@@ -385,56 +510,99 @@ def run_ours(args):
         numa_note = bind_host_thread_near_gpu(local_rank)
         ctx = ctypes.c_void_p()
         _cabi.check(lib.svbrdf_b200_ctx_create(ctypes.byref(ctx), B, N, size, size))
-        nfl = B * 12 * HW
         pin = [lib.svbrdf_b200_ctx_pinned(ctx, w) for w in range(3)]
-        ctypes.memmove(pin[0], host_in.data_ptr(), nfl * 4)
-        ctypes.memmove(pin[1], host_tg.data_ptr(), nfl * 4)
-        lossf = ctypes.c_float(0.0)
+        res3 = (ctypes.c_float * 3)()
         e2e_steps = max(3, min(steps, 20))
+        to10 = lambda m: torch.cat((m[:, 0:7], m[:, 9:12]), dim=1).contiguous()
+        host_enc = (torch.rand(B, 9, size, size, generator=torch.Generator().manual_seed(77 + rank)) * 1.8 - 0.9)
 
-        def e2e_step(i):
-            rec = records[i % len(records)]
-            _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], B, rec.data_ptr(), N,
-                                                            ctypes.byref(lossf), pin[2]))
-        for i in range(3):
-            e2e_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        # informational: the same call when the gradient is left on the device (what a training loop does with it)
-        def e2e_step_nograd(i):
-            rec = records[i % len(records)]
-            _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], B, rec.data_ptr(), N, ctypes.byref(lossf), None))
-        for i in range(2):
-            e2e_step_nograd(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step_nograd(i)
-        torch.cuda.synchronize()
-        dt_ng = time.perf_counter() - t0
-        # parity of the two entry points on the same inputs (bitwise: same kernels, same coordinates)
+        def host_leg(a_host, la, b_host, lb, l1w, with_grad, n_steps):
+            """Times svbrdf_b200_loss_host with the context's own pinned buffers (filled here, outside the timed region)."""
+            ctypes.memmove(pin[0], a_host.data_ptr(), a_host.numel() * 4)
+            ctypes.memmove(pin[1], b_host.data_ptr(), b_host.numel() * 4)
+
+            def one(i):
+                rec = records[i % len(records)]
+                _cabi.check(lib.svbrdf_b200_loss_host(ctx, pin[0], la, pin[1], lb, B, rec.data_ptr(), N, l1w, res3,
+                                                      pin[2] if with_grad else None))
+            for i in range(3):
+                one(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_steps):
+                one(i)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item()) / n_steps
+            h2d = (a_host.numel() + b_host.numel()) * 4
+            d2h = (a_host.numel() * 4 if with_grad else 0) + 12
+            return {"value": world * evals_per_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_steps,
+                    "pcie_GBps_per_gpu_both_directions": (h2d + d2h) / dt / 1e9}, float(res3[0])
+
+        in10, tg10 = to10(host_in), to10(host_tg)
+        e10, loss10 = host_leg(in10, 10, tg10, 10, -1.0, True, e2e_steps)
+        e12, loss12 = host_leg(host_in, 12, host_tg, 12, -1.0, True, e2e_steps)
+        e9, _ = host_leg(host_enc, 9, tg10, 10, 0.1, True, e2e_steps)
+        eng, _ = host_leg(in10, 10, tg10, 10, -1.0, False, e2e_steps)
+        # parity of host and device entry points on the same inputs (bitwise: same kernels, same coordinates)
         step(0)
         torch.cuda.synchronize()
-        rec0 = records[0]
-        _cabi.check(lib.svbrdf_b200_rendering_loss_host(ctx, pin[0], pin[1], B, rec0.data_ptr(), N, ctypes.byref(lossf), pin[2]))
-        same = abs(lossf.value - float(loss.item())) <= 1e-7 * abs(float(loss.item()))
+        ctypes.memmove(pin[0], host_in.data_ptr(), host_in.numel() * 4)
+        ctypes.memmove(pin[1], host_tg.data_ptr(), host_tg.numel() * 4)
+        _cabi.check(lib.svbrdf_b200_loss_host(ctx, pin[0], 12, pin[1], 12, B, records[0].data_ptr(), N, -1.0, res3, pin[2]))
+        same = abs(res3[0] - float(loss.item())) <= 1e-7 * abs(float(loss.item())) and loss10 == loss12
         lib.svbrdf_b200_ctx_destroy(ctx)
+
+        # the path a caller of the reference interface takes with PAGEABLE CPU tensors: RenderingLoss(LocalRenderer())(x, t)
+        # + backward(), scene sampling (reference order) included; tensors staged through pinned double buffers both ways
+        pageable = None
+        if world == 1:
+            import svbrdf_estimation_b200 as S
+            mod = S.RenderingLoss(S.LocalRenderer())
+            xin = host_in.clone().requires_grad_(True)
+
+            def api_step():
+                xin.grad = None
+                mod(xin, host_tg).backward()
+            for _ in range(2):
+                api_step()
+            torch.cuda.synchronize()
+            n_api = max(3, min(steps, 8))
+            t0 = time.perf_counter()
+            for _ in range(n_api):
+                api_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_api
+            pageable = {"value": evals_per_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_api,
+                        "call": "RenderingLoss(LocalRenderer())(cpu_input, cpu_target).backward() with pageable [64,12,256,256] CPU tensors "
+                                "(renderers.host_to_device -> staging.upload / download: 32 MB pinned double buffers)",
+                        "h2d_bytes_per_step": 2 * host_in.numel() * 4, "d2h_bytes_per_step": host_in.numel() * 4 + 4}
         os.sched_setaffinity(0, all_cpus)           # the CPU baseline below uses every host thread again
-        e2e = {"value": world * evals_per_step / (dt / e2e_steps) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": 2 * nfl * 4, "d2h_bytes_per_step": nfl * 4 + 4, "steps": e2e_steps,
-               "ms_per_step": dt / e2e_steps * 1e3, "entry": "svbrdf_b200_rendering_loss_host (pinned host maps -> loss + grad on host)",
-               "matches_device_entry": bool(same), "host_placement": numa_note,
-               "loss_only_variant": {"value": evals_per_step / (dt_ng / e2e_steps) / 1e9, "unit": UNIT, "ms_per_step": dt_ng / e2e_steps * 1e3,
-                                     "d2h_bytes_per_step": 4, "note": "per rank; forward only (no gradient is computed or downloaded): "
-                                     "the upload alone, i.e. the PCIe floor of this entry point"}}
+        e2e = dict(e10)
+        e2e.update({"entry": "svbrdf_b200_loss_host, SVBRDF_LAYOUT_MAPS10 input/target/gradient (roughness stored once: the model and the "
+                             "dataset replicate it, utils.py:78-80): host maps -> loss + gradient on the host, 16 batch slices pipelined "
+                             "over H2D / compute / D2H streams",
+                    "host_buffers": "the context's own PINNED buffers (svbrdf_b200_ctx_pinned), filled before the timed region; every step "
+                                    "copies them to the device, computes, and copies loss + gradient back inside the timed region",
+                    "matches_device_entry": bool(same), "host_placement": numa_note,
+                    "maps12_variant": dict(e12, note="same call with the reference's 12-channel tensors (SVBRDF_LAYOUT_MAPS12): 36 instead of 30 planes per step"),
+                    "encoded9_variant": dict(e9, note="MixedLoss on the 9-channel network output + 10-channel target (28 planes per step)"),
+                    "loss_only_variant": dict(eng, note="forward only (no gradient computed or downloaded): the upload alone, i.e. the PCIe floor of this entry point"),
+                    "python_api_pageable_tensors": pageable})
+
+    # ---- configs[4]: the full training step, global batch 256 strong-scaled over the ranks (all ranks take part) ----
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = train_step_c5(args, torch, dist, dev, world, rank, local_rank)
+        except Exception as exc:                  # never lose the headline line over the informational leg
+            if world > 1:
+                raise
+            c5 = {"unavailable": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -478,10 +646,11 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, sec, b, threads = time_cpu_port(args.workload, 15, 1, budget_s=40.0)
-        cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "first %d of %d maps of the workload, %dx%d, N=%d, 1 warm-up + 15 timed fwd+bwd passes (%.2f s each)"
-                         % (b, B, size, size, N, sec)}
+        val, sec, b, threads, kind = time_cpu_port(args.workload, 5, 1, budget_s=40.0, full_batch=True)
+        cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%s, %dx%d, N=%d, 1 warm-up + 5 timed fwd+bwd passes (%.2f s each)"
+                         % ("the whole batch of the workload (%d maps)" % B if b == B else "first %d of %d maps of the workload" % (b, B),
+                            size, size, N, sec)}
 
     eager = None
     if world == 1 and not args.no_cpu_baseline:
@@ -501,7 +670,7 @@ def run_ours(args):
                        "scene_sampler_ms_per_step_host": sampler_ms},
             "value_per_gpu": value / world, "loss": loss_value,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_register_file": roofline_rf, "fp32_probes_tflops": probes,
-            "accurate_variant": accurate,
+            "accurate_variant": accurate, "train_step_c5": c5,
             "cpu_baseline": cpu, "reference_port_eager_on_gpu": eager, "e2e": e2e, "gpu_launches": 2 * steps,
             "gpu_launches_note": "per step: 1 fused loss fwd+bwd kernel + 1 single-CTA finalize kernel",
             "clocks": sampler.summary(clock_note),
@@ -535,6 +704,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] training-step leg")
+    ap.add_argument("--c5-global-batch", type=int, default=256)
+    ap.add_argument("--c5-steps", type=int, default=6)
     args = ap.parse_args()
     args.out = OnlyJsonOnStdout()
     if args.impl == "reference":

@@ -183,6 +183,25 @@ SVBRDF_API int svbrdf_b200_mixed_loss_encoded_forward_backward(const float* enco
                                             float* grad_encoded_dev, void* workspace_dev,
                                             size_t workspace_bytes, void* stream);
 
+/* ---- channel layouts -------------------------------------------------------------------------------------
+ * The reference's tensors carry 12 channels of which the three roughness channels are replicas of one map
+ * (utils.py:78-80: the model and the dataset repeat it), and the network itself emits 9 (models.py:334-346).  Callers
+ * that know this can hand over fewer bytes; the gradient comes back in the input's layout.
+ *   SVBRDF_LAYOUT_MAPS12   [B,12,H,W]  normals(3) diffuse(3) roughness(3) specular(3)          utils.py:36-58
+ *   SVBRDF_LAYOUT_MAPS10   [B,10,H,W]  normals(3) diffuse(3) roughness(1) specular(3); d/d roughness = sum of the three
+ *   SVBRDF_LAYOUT_ENCODED9 [B, 9,H,W]  network output after tanh: normal xy, diffuse, roughness, specular in [-1,1]
+ * Supported (input, target): (MAPS12, MAPS12), (MAPS10, MAPS10), (ENCODED9, MAPS12), (ENCODED9, MAPS10).
+ * l1_weight < 0: RenderingLoss (losses.py:29-52); l1_weight >= 0: MixedLoss (losses.py:54-63).  ENCODED9 input exists as
+ * MixedLoss forward+backward only, MAPS10 input as RenderingLoss only.  out_dev[0..2] = loss, rendering loss, map-L1 loss;
+ * grad_input_dev (input layout) may be NULL where a forward-only form exists.                                   */
+#define SVBRDF_LAYOUT_MAPS12   12
+#define SVBRDF_LAYOUT_MAPS10   10
+#define SVBRDF_LAYOUT_ENCODED9 9
+SVBRDF_API int svbrdf_b200_loss_layouts(const float* input_dev, int input_layout, const float* target_dev, int target_layout,
+                                        int B, int H, int W, const float* scenes_host, int N, float l1_weight,
+                                        const float* lin_dev, float* out_dev, float* grad_input_dev, void* workspace_dev,
+                                        size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer entry point (the call a non-PyTorch caller makes) --------------------------
  * A context owns pinned staging buffers, device buffers and copy/compute streams for problems
  * up to the given size on the current device.  One call at a time per context (use one context per
@@ -203,6 +222,13 @@ SVBRDF_API float* svbrdf_b200_ctx_pinned(svbrdf_b200_ctx* ctx, int which);
 SVBRDF_API int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* ctx, const float* input_host,
                                     const float* target_host, int B, const float* scenes_host,
                                     int N, float* loss_host, float* grad_host);
+
+/* The same pipeline for any supported layout pair and for MixedLoss (see svbrdf_b200_loss_layouts): with MAPS10 maps a
+ * step moves 30 instead of 36 planes over PCIe, with ENCODED9 input and a MAPS10 target 28.  out_host[0..2] = loss,
+ * rendering loss, map-L1 loss; grad_host has the input's layout (NULL: no gradient, where that form exists).       */
+SVBRDF_API int svbrdf_b200_loss_host(svbrdf_b200_ctx* ctx, const float* input_host, int input_layout,
+                                    const float* target_host, int target_layout, int B, const float* scenes_host,
+                                    int N, float l1_weight, float* out_host, float* grad_host);
 
 #ifdef __cplusplus
 }

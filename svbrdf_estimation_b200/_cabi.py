@@ -59,6 +59,9 @@ PROTOTYPES = {
                                                                        ctypes.c_int, _c_float_p, ctypes.c_int,
                                                                        ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
                                                                        ctypes.c_void_p, ctypes.c_size_t, _c_stream]),
+    "svbrdf_b200_loss_layouts": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,
+                                                _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _c_stream]),
     "svbrdf_b200_ctx_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int]),
     "svbrdf_b200_ctx_destroy": (None, [ctypes.c_void_p]),
@@ -66,7 +69,10 @@ PROTOTYPES = {
     "svbrdf_b200_rendering_loss_host": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, ctypes.c_int,
                                                        _c_float_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                                        _c_float_p]),
+    "svbrdf_b200_loss_host": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                             _c_float_p, ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p]),
 }
+LAYOUT_MAPS12, LAYOUT_MAPS10, LAYOUT_ENCODED9 = 12, 10, 9
 
 _lib = None
 _lock = threading.Lock()

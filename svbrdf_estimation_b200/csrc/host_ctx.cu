@@ -182,19 +182,23 @@ extern "C" float* svbrdf_b200_ctx_pinned(svbrdf_b200_ctx* c, int which) {
     return which == 0 ? c->h_in : which == 1 ? c->h_tg : which == 2 ? c->h_gr : nullptr;
 }
 
-extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* input_host, const float* target_host,
-                                               int B, const float* scenes_host, int N, float* loss_host,
-                                               float* grad_host) {
+static int loss_host_impl(svbrdf_b200_ctx* c, const float* input_host, int input_layout, const float* target_host,
+                          int target_layout, int B, const float* scenes_host, int N, float l1_weight, float* out_host,
+                          int n_out, float* grad_host) {
     if (!c) return svb_fail(SVBRDF_E_STATE, "context is null");
-    if (!input_host || !target_host || !scenes_host || !loss_host)
+    if (!input_host || !target_host || !scenes_host || !out_host)
         return svb_fail(SVBRDF_E_INVALID, "null pointer argument");
     if (B <= 0 || B > c->max_B || N <= 0 || N > c->max_N)
         return svb_fail(SVBRDF_E_INVALID, "B or N exceeds what the context was created for");
+    const int lay = svb_layout_id(input_layout, target_layout);
+    const bool mixed = l1_weight >= 0.f;
+    if (int e = svb_check_layout_form(lay, mixed, grad_host != nullptr)) return e;
     int rc = 0, prev = -1;
     cudaGetDevice(&prev);
     const int HW = c->H * c->W;
     const bool packed = (c->W & 1) == 0;          // cudaMalloc'd buffers: aligned
     const int cpi = svb_ctas_per_image(HW, packed);
+    const size_t in_floats = (size_t)input_layout * HW, tg_floats = (size_t)target_layout * HW;   // per batch element
     float* part_render = c->d_ws;
     float* part_l1 = c->d_ws + (size_t)B * cpi;
     // slices: enough to overlap the two copy directions with compute, not so many that launch
@@ -204,31 +208,49 @@ extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* 
         CK(cudaSetDevice(c->device));
         for (int i = 0; i < slices; ++i) {
             const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
-            const size_t off = (size_t)b0 * c->map_floats, cnt = (size_t)(b1 - b0) * c->map_floats;
-            CK(cudaMemcpyAsync(c->d_in + off, input_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
-            CK(cudaMemcpyAsync(c->d_tg + off, target_host + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d2));
+            CK(cudaMemcpyAsync(c->d_in + b0 * in_floats, input_host + b0 * in_floats, (b1 - b0) * in_floats * sizeof(float),
+                               cudaMemcpyHostToDevice, c->s_h2d));
+            CK(cudaMemcpyAsync(c->d_tg + b0 * tg_floats, target_host + b0 * tg_floats, (b1 - b0) * tg_floats * sizeof(float),
+                               cudaMemcpyHostToDevice, c->s_h2d2));
             CK(cudaEventRecord(c->ev_up[i], c->s_h2d));
             CK(cudaEventRecord(c->ev_up2[i], c->s_h2d2));
             CK(cudaStreamWaitEvent(c->s_comp, c->ev_up[i], 0));
             CK(cudaStreamWaitEvent(c->s_comp, c->ev_up2[i], 0));
             rc = svb_launch_loss_range(c->d_in, c->d_tg, grad_host ? c->d_gr : nullptr, B, HW, c->W, scenes_host, N,
-                                       c->d_lin, part_render, part_l1, false, 0.f, b0, b1 - b0, c->s_comp, packed);
+                                       c->d_lin, part_render, part_l1, mixed, mixed ? l1_weight : 0.f, b0, b1 - b0, c->s_comp,
+                                       packed, lay);
             if (rc) goto done;
             if (grad_host) {
                 CK(cudaEventRecord(c->ev_k[i], c->s_comp));
                 CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[i], 0));
-                CK(cudaMemcpyAsync(grad_host + off, c->d_gr + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+                CK(cudaMemcpyAsync(grad_host + b0 * in_floats, c->d_gr + b0 * in_floats, (b1 - b0) * in_floats * sizeof(float),
+                                   cudaMemcpyDeviceToHost, c->s_d2h));
             }
         }
-        rc = svb_launch_finalize(part_render, part_l1, B, HW, packed, N, false, 0.f, c->d_loss, 1, c->s_comp);
+        rc = svb_launch_finalize(part_render, part_l1, B, HW, packed, N, mixed, mixed ? l1_weight : 0.f, c->d_loss, 3, c->s_comp);
         if (rc) goto done;
-        CK(cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
+        CK(cudaMemcpyAsync(c->h_loss, c->d_loss, 3 * sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
         CK(cudaStreamSynchronize(c->s_comp));
         CK(cudaStreamSynchronize(c->s_d2h));
-        *loss_host = c->h_loss[0];
+        for (int i = 0; i < n_out; ++i) out_host[i] = c->h_loss[i];
     }
 done:
     if (rc) { cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_h2d2); cudaStreamSynchronize(c->s_comp); cudaStreamSynchronize(c->s_d2h); }
     if (prev >= 0) cudaSetDevice(prev);
     return rc;
+}
+
+extern "C" int svbrdf_b200_rendering_loss_host(svbrdf_b200_ctx* c, const float* input_host, const float* target_host,
+                                               int B, const float* scenes_host, int N, float* loss_host,
+                                               float* grad_host) {
+    if (!loss_host) return svb_fail(SVBRDF_E_INVALID, "null pointer argument");
+    return loss_host_impl(c, input_host, SVBRDF_LAYOUT_MAPS12, target_host, SVBRDF_LAYOUT_MAPS12, B, scenes_host, N, -1.f,
+                          loss_host, 1, grad_host);
+}
+
+extern "C" int svbrdf_b200_loss_host(svbrdf_b200_ctx* c, const float* input_host, int input_layout, const float* target_host,
+                                     int target_layout, int B, const float* scenes_host, int N, float l1_weight,
+                                     float* out_host, float* grad_host) {
+    return loss_host_impl(c, input_host, input_layout, target_host, target_layout, B, scenes_host, N, l1_weight, out_host, 3,
+                          grad_host);
 }

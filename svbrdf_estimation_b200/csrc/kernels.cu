@@ -100,6 +100,27 @@ __device__ __forceinline__ void store12(float* __restrict__ base, int HW, const 
     for (int c = 0; c < 12; ++c) st_stream(base + (size_t)c * HW, v[c]);
 }
 
+// 10-channel layout [n(3) d(3) r(1) s(3)]: the information content of the 12-channel contract when the three roughness
+// channels are replicas of one map, which is what the model and the dataset produce (utils.py:78-80).  The kernels work
+// on the 12-channel form in registers; the gradient of the single roughness channel is the sum of the three.
+template <typename T>
+__device__ __forceinline__ void load10(const float* __restrict__ base, int HW, T (&v)[12]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ld_lane(base + (size_t)c * HW, v[c]);
+    ld_lane(base + (size_t)6 * HW, v[6]);
+    v[7] = v[6]; v[8] = v[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ld_lane(base + (size_t)(7 + c) * HW, v[9 + c]);
+}
+template <typename T>
+__device__ __forceinline__ void store10(float* __restrict__ base, int HW, const T (&v)[12]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st_stream(base + (size_t)c * HW, v[c]);
+    st_stream(base + (size_t)6 * HW, (v[6] + v[7]) + v[8]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st_stream(base + (size_t)(7 + c) * HW, v[9 + c]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -155,6 +176,11 @@ __device__ __forceinline__ Where<T> locate(int HW, int W, const float* __restric
 // and read back in the record loop with three broadcast LDS.128, instead of 7 indexed constant loads and 7 scalar
 // FP operations per thread and record.  Same operations on the same values: bit-identical to the other path.
 constexpr int kRowTabMaxN = 64;
+// (input, target) channel layouts of a loss launch; the gradient has the input's layout
+constexpr int kLay12 = 0;      // [B,12,H,W] maps, [B,12,H,W] target                      (the reference's tensors)
+constexpr int kLayEnc12 = 1;   // [B,9,H,W] encoded network output, [B,12,H,W] target
+constexpr int kLay10 = 2;      // [B,10,H,W] maps, [B,10,H,W] target                      (roughness stored once)
+constexpr int kLayEnc10 = 3;   // [B,9,H,W] encoded network output, [B,10,H,W] target
 struct RowTabRecs {
     const float4* tab;     // [N][3]
     __device__ __forceinline__ RecScalars get(int k) const {
@@ -168,16 +194,16 @@ struct RowTabRecs {
 };
 extern __shared__ float4 svb_rowtab[];
 
-#ifdef SVB_LOSS_MAXNREG         // A/B builds: an explicit register cap instead of the one implied by kMinBlocks
-#define SVB_LOSS_BOUNDS __maxnreg__(SVB_LOSS_MAXNREG)
-#else
-#define SVB_LOSS_BOUNDS __launch_bounds__(Cfg<T>::kThreads, Cfg<T>::kMinBlocks)
-#endif
-template <typename T, bool BWD, bool MIXED, bool GREY, bool ENC, int CAP, bool ACC = false, bool ROWTAB = false>
-__global__ void SVB_LOSS_BOUNDS
-loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
+// The per-thread work of the loss kernels (both lane types).  Register budget: the packed kernels are capped at 160
+// registers per thread with __maxnreg__ (3 CTAs of 128 threads per SM would allow 168; ptxas settles on 158 and finds
+// a 2 % faster schedule there - measured on B200 for caps 144 ... 168, profiles/r2_variants.txt), the
+// one-pixel-per-thread kernels at 128 (2 CTAs of 256 threads).
+template <typename T, bool BWD, bool MIXED, bool GREY, int LAY, int CAP, bool ACC, bool ROWTAB>
+__device__ __forceinline__ void loss_body(const LossArgs& a, const SceneBlock<CAP>& sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
-    constexpr int CIN = ENC ? 9 : 12;
+    constexpr bool ENC = LAY == kLayEnc12 || LAY == kLayEnc10;
+    constexpr int CIN = LAY == kLay12 ? 12 : (LAY == kLay10 ? 10 : 9);       // channels of `input` and of `grad`
+    constexpr int CTG = (LAY == kLay10 || LAY == kLayEnc10) ? 10 : 12;         // channels of `target`
     __shared__ float red[THREADS / 32];
     // Programmatic dependent launch: the finalize kernel queued behind this grid may be scheduled as soon as
     // every CTA of this grid is resident (it then waits in griddepcontrol.wait for this grid to complete and
@@ -185,7 +211,7 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     asm volatile("griddepcontrol.launch_dependents;");
     const int b = blockIdx.y;
     const Where<T> w = locate<T>(a.HW, a.W, a.lin);
-    const size_t off = (size_t)b * 12 * a.HW + w.p;
+    const size_t off_tg = (size_t)b * CTG * a.HW + w.p;
     const size_t off_in = (size_t)b * CIN * a.HW + w.p;
     T vi[12], vt[12], g[12], inv_len;
     if (ENC) {
@@ -193,10 +219,13 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) ld_lane(a.input + off_in + (size_t)c * a.HW, e[c]);
         decode_encoded<T>(e, vi, inv_len);
+    } else if (CIN == 10) {
+        load10<T>(a.input + off_in, a.HW, vi);
     } else {
-        load12<T>(a.input + off, a.HW, vi);
+        load12<T>(a.input + off_in, a.HW, vi);
     }
-    load12<T>(a.target + off, a.HW, vt);
+    if (CTG == 10) load10<T>(a.target + off_tg, a.HW, vt);
+    else load12<T>(a.target + off_tg, a.HW, vt);
     const float* rec = sc.v + (size_t)b * a.N * kRecFloats;
 
     T lsum;
@@ -222,8 +251,10 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
             encode_grad<T>(vi, inv_len, g, ge);
 #pragma unroll
             for (int c = 0; c < 9; ++c) st_stream(a.grad + off_in + (size_t)c * a.HW, ge[c]);
+        } else if (CIN == 10) {
+            store10<T>(a.grad + off_in, a.HW, g);
         } else {
-            store12<T>(a.grad + off, a.HW, g);
+            store12<T>(a.grad + off_in, a.HW, g);
         }
     }
 
@@ -234,6 +265,20 @@ loss_kernel(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
         const float tl = cta_sum<THREADS>(w.live ? hsum(l1) : 0.f, red);
         if (threadIdx.x == 0) a.part_l1[cta] = tl;
     }
+}
+
+#ifndef SVB_LOSS_MAXNREG
+#define SVB_LOSS_MAXNREG 160
+#endif
+template <typename T, bool BWD, bool MIXED, bool GREY, int LAY, int CAP, bool ACC = false, bool ROWTAB = false>
+__global__ void __maxnreg__(SVB_LOSS_MAXNREG)
+loss_kernel_packed(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
+    loss_body<T, BWD, MIXED, GREY, LAY, CAP, ACC, ROWTAB>(a, sc);
+}
+template <typename T, bool BWD, bool MIXED, bool GREY, int LAY, int CAP, bool ACC = false, bool ROWTAB = false>
+__global__ void __launch_bounds__(Cfg<float>::kThreads, Cfg<float>::kMinBlocks)
+loss_kernel_scalar(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
+    loss_body<T, BWD, MIXED, GREY, LAY, CAP, ACC, ROWTAB>(a, sc);
 }
 
 // out[0] = mixed (or rendering) loss, out[1] = rendering loss, out[2] = map-L1 loss (MIXED only).
@@ -455,36 +500,50 @@ struct LossSel {
     bool small;     // records fit the small parameter block
 };
 
-template <typename T, bool BWD, bool MIXED, bool ENC, bool ACC>
+template <typename T, bool BWD, bool MIXED, int LAY, bool ACC>
 static cudaError_t launch_loss_v(const LossSel& sel, dim3 grid, const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
     constexpr int TH = Cfg<T>::kThreads;
     constexpr bool kPacked = LaneTraits<T>::kLanes == 2;
+    constexpr bool ENC = LAY != kLay12;          // only the 12-channel layout has small-parameter-block kernels
     const size_t smem = (size_t)(TH / 32) * 3 * a.N * sizeof(float4);
-#define SVB_GO(CAP, GREY, ROW) launch_with_scenes<CAP, TH>(loss_kernel<T, BWD, MIXED, GREY, ENC, CAP, ACC, ROW>, grid, a, recs, nrec, st, (ROW) ? smem : 0)
+#define SVB_GO_K(KERNEL, CAP, GREY, ROW) launch_with_scenes<CAP, TH>(KERNEL<T, BWD, MIXED, GREY, LAY, CAP, ACC, ROW>, grid, a, recs, nrec, st, (ROW) ? smem : 0)
     if constexpr (kPacked) {
+#define SVB_GO(CAP, GREY, ROW) SVB_GO_K(loss_kernel_packed, CAP, GREY, ROW)
         if (sel.grey && sel.rowtab) {          // what RenderingLoss / MixedLoss launch on every power-of-two map size
             if constexpr (ENC) return SVB_GO(kCapLarge, true, true);
             else return sel.small ? SVB_GO(kCapSmall, true, true) : SVB_GO(kCapLarge, true, true);
         }
-    }
-    if constexpr (ENC) return sel.grey ? SVB_GO(kCapLarge, true, false) : SVB_GO(kCapLarge, false, false);
-    else {
-        if (sel.grey) return sel.small ? SVB_GO(kCapSmall, true, false) : SVB_GO(kCapLarge, true, false);
-        return sel.small ? SVB_GO(kCapSmall, false, false) : SVB_GO(kCapLarge, false, false);
-    }
+        if constexpr (ENC) return sel.grey ? SVB_GO(kCapLarge, true, false) : SVB_GO(kCapLarge, false, false);
+        else {
+            if (sel.grey) return sel.small ? SVB_GO(kCapSmall, true, false) : SVB_GO(kCapLarge, true, false);
+            return sel.small ? SVB_GO(kCapSmall, false, false) : SVB_GO(kCapLarge, false, false);
+        }
 #undef SVB_GO
+    } else {
+#define SVB_GO(CAP, GREY, ROW) SVB_GO_K(loss_kernel_scalar, CAP, GREY, ROW)
+        if constexpr (ENC) return sel.grey ? SVB_GO(kCapLarge, true, false) : SVB_GO(kCapLarge, false, false);
+        else {
+            if (sel.grey) return sel.small ? SVB_GO(kCapSmall, true, false) : SVB_GO(kCapLarge, true, false);
+            return sel.small ? SVB_GO(kCapSmall, false, false) : SVB_GO(kCapLarge, false, false);
+        }
+#undef SVB_GO
+    }
+#undef SVB_GO_K
 }
 
 template <typename T>
-static cudaError_t launch_loss_t(bool bwd, bool mixed, bool encoded, bool accurate, const LossSel& sel, dim3 grid,
+static cudaError_t launch_loss_t(bool bwd, bool mixed, int lay, bool accurate, const LossSel& sel, dim3 grid,
                                  const LossArgs& a, const float* recs, int nrec, cudaStream_t st) {
-    if (encoded) return launch_loss_v<T, true, true, true, false>(sel, grid, a, recs, nrec, st);
-    if (accurate) return bwd ? launch_loss_v<T, true, false, false, true>(sel, grid, a, recs, nrec, st)
-                             : launch_loss_v<T, false, false, false, true>(sel, grid, a, recs, nrec, st);
-    if (bwd) return mixed ? launch_loss_v<T, true, true, false, false>(sel, grid, a, recs, nrec, st)
-                          : launch_loss_v<T, true, false, false, false>(sel, grid, a, recs, nrec, st);
-    return mixed ? launch_loss_v<T, false, true, false, false>(sel, grid, a, recs, nrec, st)
-                 : launch_loss_v<T, false, false, false, false>(sel, grid, a, recs, nrec, st);
+    if (lay == kLayEnc12) return launch_loss_v<T, true, true, kLayEnc12, false>(sel, grid, a, recs, nrec, st);
+    if (lay == kLayEnc10) return launch_loss_v<T, true, true, kLayEnc10, false>(sel, grid, a, recs, nrec, st);
+    if (lay == kLay10) return bwd ? launch_loss_v<T, true, false, kLay10, false>(sel, grid, a, recs, nrec, st)
+                                  : launch_loss_v<T, false, false, kLay10, false>(sel, grid, a, recs, nrec, st);
+    if (accurate) return bwd ? launch_loss_v<T, true, false, kLay12, true>(sel, grid, a, recs, nrec, st)
+                             : launch_loss_v<T, false, false, kLay12, true>(sel, grid, a, recs, nrec, st);
+    if (bwd) return mixed ? launch_loss_v<T, true, true, kLay12, false>(sel, grid, a, recs, nrec, st)
+                          : launch_loss_v<T, true, false, kLay12, false>(sel, grid, a, recs, nrec, st);
+    return mixed ? launch_loss_v<T, false, true, kLay12, false>(sel, grid, a, recs, nrec, st)
+                 : launch_loss_v<T, false, false, kLay12, false>(sel, grid, a, recs, nrec, st);
 }
 
 // Enqueues the loss kernel for batch elements [b0, b0+bn) of a B-element problem (several launches if
@@ -492,16 +551,17 @@ static cudaError_t launch_loss_t(bool bwd, bool mixed, bool encoded, bool accura
 // svb_loss_packed() of those pointers (the caller sizes the partial arrays with the same value).
 int svb_launch_loss_range(const float* input, const float* target, float* grad, int B, int HW, int W,
                           const float* scenes, int N, const float* lin, float* part_render, float* part_l1,
-                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool packed, bool encoded,
+                          bool mixed, float l1_weight, int b0, int bn, cudaStream_t st, bool packed, int lay,
                           bool accurate) {
-    const int cin = encoded ? 9 : 12;
+    const int cin = lay == kLay12 ? 12 : (lay == kLay10 ? 10 : 9);
+    const int ctg = (lay == kLay10 || lay == kLayEnc10) ? 10 : 12;
     const int cpi = svb_ctas_per_image(HW, packed);
     LossArgs a;
     a.lin = lin; a.HW = HW; a.W = W; a.N = N;
     a.scale_render = (float)(1.0 / ((double)B * N * 3.0 * HW));
     a.scale_l1 = (float)((double)l1_weight / ((double)B * 3.0 * HW));
     LossSel sel;
-    sel.small = !encoded && (size_t)bn * N <= (size_t)kCapSmall;
+    sel.small = lay == kLay12 && (size_t)bn * N <= (size_t)kCapSmall;
 #ifdef SVB_NO_ROWTAB            // A/B builds (scripts/variant_bench.py)
     sel.rowtab = false;
 #else
@@ -511,15 +571,15 @@ int svb_launch_loss_range(const float* input, const float* target, float* grad, 
     for (int s0 = b0; s0 < b0 + bn; s0 += bc_max) {
         const int bc = (b0 + bn - s0 < bc_max) ? (b0 + bn - s0) : bc_max;
         a.input = input + (size_t)s0 * cin * HW;
-        a.target = target + (size_t)s0 * 12 * HW;
+        a.target = target + (size_t)s0 * ctg * HW;
         a.grad = grad ? grad + (size_t)s0 * cin * HW : nullptr;
         a.part_render = part_render + (size_t)s0 * cpi;
         a.part_l1 = part_l1 + (size_t)s0 * cpi;
         const dim3 grid(cpi, bc);
         const float* recs = scenes + (size_t)s0 * N * kRecFloats;
         sel.grey = all_grey(recs, bc * N);
-        const cudaError_t e = packed ? launch_loss_t<F2>(grad != nullptr, mixed, encoded, accurate, sel, grid, a, recs, bc * N, st)
-                                     : launch_loss_t<float>(grad != nullptr, mixed, encoded, accurate, sel, grid, a, recs, bc * N, st);
+        const cudaError_t e = packed ? launch_loss_t<F2>(grad != nullptr, mixed, lay, accurate, sel, grid, a, recs, bc * N, st)
+                                     : launch_loss_t<float>(grad != nullptr, mixed, lay, accurate, sel, grid, a, recs, bc * N, st);
         if (e != cudaSuccess) return cuda_status(e, "loss_kernel launch");
     }
     return 0;
@@ -545,7 +605,7 @@ int svb_launch_finalize(const float* part_render, const float* part_l1, int B, i
 
 static int loss_impl(const float* input, const float* target, int B, int H, int W, const float* scenes, int N,
                      const float* lin, float* out, int n_out, float* grad, void* ws, size_t ws_bytes,
-                     bool mixed, float l1_weight, void* stream, bool encoded = false, bool accurate = false) {
+                     bool mixed, float l1_weight, void* stream, int lay = kLay12, bool accurate = false) {
     if (int e = svb_check_shape(B, H, W, N)) return e;
     if (!input || !target || !scenes || !lin || !out || !ws) return fail(SVBRDF_E_INVALID, "null pointer argument");
     if (ws_bytes < svbrdf_b200_workspace_bytes(B, N, H, W)) return fail(SVBRDF_E_INVALID, "workspace too small");
@@ -557,7 +617,7 @@ static int loss_impl(const float* input, const float* target, int B, int H, int 
     float* part_render = (float*)ws;
     float* part_l1 = part_render + (size_t)B * svb_ctas_per_image(HW, packed);
     if (int e = svb_launch_loss_range(input, target, grad, B, HW, W, scenes, N, lin, part_render, part_l1, mixed,
-                                      l1_weight, 0, B, st, packed, encoded, accurate))
+                                      l1_weight, 0, B, st, packed, lay, accurate))
         return e;
     return svb_launch_finalize(part_render, part_l1, B, HW, packed, N, mixed, l1_weight, out, n_out, st);
 }
@@ -584,14 +644,14 @@ extern "C" int svbrdf_b200_loss_forward_backward_accurate(const float* input_dev
                                                           size_t workspace_bytes, void* stream) {
     if (!grad_input_dev) return fail(SVBRDF_E_INVALID, "grad_input_dev is null");
     return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, grad_input_dev,
-                     workspace_dev, workspace_bytes, false, 0.f, stream, false, true);
+                     workspace_dev, workspace_bytes, false, 0.f, stream, kLay12, true);
 }
 
 extern "C" int svbrdf_b200_loss_forward_accurate(const float* input_dev, const float* target_dev, int B, int H, int W,
                                                  const float* scenes_host, int N, const float* lin_dev, float* loss_dev,
                                                  void* workspace_dev, size_t workspace_bytes, void* stream) {
     return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, loss_dev, 1, nullptr, workspace_dev,
-                     workspace_bytes, false, 0.f, stream, false, true);
+                     workspace_bytes, false, 0.f, stream, kLay12, true);
 }
 
 extern "C" int svbrdf_b200_mixed_loss_forward_backward(const float* input_dev, const float* target_dev, int B, int H,
@@ -609,7 +669,36 @@ extern "C" int svbrdf_b200_mixed_loss_encoded_forward_backward(const float* enco
                                                                size_t workspace_bytes, void* stream) {
     if (!grad_encoded_dev) return fail(SVBRDF_E_INVALID, "grad_encoded_dev is null");
     return loss_impl(encoded_dev, target_dev, B, H, W, scenes_host, N, lin_dev, out_dev, 3, grad_encoded_dev,
-                     workspace_dev, workspace_bytes, true, l1_weight, stream, true);
+                     workspace_dev, workspace_bytes, true, l1_weight, stream, kLayEnc12);
+}
+
+// (input layout, target layout) -> kernel layout id, or -1
+int svb_layout_id(int input_layout, int target_layout) {
+    if (input_layout == SVBRDF_LAYOUT_MAPS12 && target_layout == SVBRDF_LAYOUT_MAPS12) return kLay12;
+    if (input_layout == SVBRDF_LAYOUT_ENCODED9 && target_layout == SVBRDF_LAYOUT_MAPS12) return kLayEnc12;
+    if (input_layout == SVBRDF_LAYOUT_MAPS10 && target_layout == SVBRDF_LAYOUT_MAPS10) return kLay10;
+    if (input_layout == SVBRDF_LAYOUT_ENCODED9 && target_layout == SVBRDF_LAYOUT_MAPS10) return kLayEnc10;
+    return -1;
+}
+// Which loss forms exist for a layout: the encoded-input kernels are MixedLoss forward+backward only, the 10-channel
+// maps kernels RenderingLoss only.  Returns 0 or sets the error.
+int svb_check_layout_form(int lay, bool mixed, bool has_grad) {
+    if (lay < 0) return fail(SVBRDF_E_INVALID, "unsupported (input, target) layout combination");
+    if ((lay == kLayEnc12 || lay == kLayEnc10) && !(mixed && has_grad))
+        return fail(SVBRDF_E_INVALID, "encoded input: only the MixedLoss forward+backward form exists (l1_weight >= 0, gradient buffer)");
+    if (lay == kLay10 && mixed) return fail(SVBRDF_E_INVALID, "10-channel maps: only the RenderingLoss forms exist (l1_weight < 0)");
+    return 0;
+}
+
+extern "C" int svbrdf_b200_loss_layouts(const float* input_dev, int input_layout, const float* target_dev, int target_layout,
+                                        int B, int H, int W, const float* scenes_host, int N, float l1_weight,
+                                        const float* lin_dev, float* out_dev, float* grad_input_dev, void* workspace_dev,
+                                        size_t workspace_bytes, void* stream) {
+    const int lay = svb_layout_id(input_layout, target_layout);
+    const bool mixed = l1_weight >= 0.f;
+    if (int e = svb_check_layout_form(lay, mixed, grad_input_dev != nullptr)) return e;
+    return loss_impl(input_dev, target_dev, B, H, W, scenes_host, N, lin_dev, out_dev, 3, grad_input_dev, workspace_dev,
+                     workspace_bytes, mixed, mixed ? l1_weight : 0.f, stream, lay);
 }
 
 template <typename T>

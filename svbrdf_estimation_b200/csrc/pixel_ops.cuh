@@ -74,8 +74,13 @@ SVB_DEV T loss_records(const Pix<T, NC>& pi, const Pix<T, NC>& pt, T x, const RS
 #else
         constexpr bool kAcc = ACC;
 #endif
+#ifdef SVB_TARGET_FIRST         // A/B builds: source order of the two independent forward evaluations
+        shade_fwd<T, NC, false, kAcc>(g, pt, ft);
+        shade_fwd<T, NC, BWD, kAcc>(g, pi, fi);
+#else
         shade_fwd<T, NC, BWD, kAcc>(g, pi, fi);
         shade_fwd<T, NC, false, kAcc>(g, pt, ft);
+#endif
         // radiance + 0.1 of both maps (losses.py:46-47); E = light colour * falloff / pi
         T E[NC], fin[NC], xi[NC], xt[NC];
         if (GREY) {

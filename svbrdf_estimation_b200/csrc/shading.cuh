@@ -400,8 +400,13 @@ SVB_DEV void shade_bwd(const Geo<T>& g, const Pix<T, NC>& p, const Fwd<T>& o, co
     // d ln S / d NH = 4 NH (1-a2) / q [q unclamped];  d ln S / d VN = -(wV + VN (1-a2)) zV;  same for LN.
     // clamp(min=...) passes the gradient where the raw value is >= the bound (renderers.py:48-52,96).
     const T gNHr = (G * (p.oma2 * w)) * vstep(o.NHr, kClamp, 2.f);
+#ifdef SVB_MASK_SELECT          // A/B builds: compare + select per lane (ALU pipe) instead of a 0/1 factor (FMA pipe)
+    const T gVNp = vsel(vge(o.VNr, kClamp), G * (vfma(o.VN, p.oma2, o.wV) * o.zV), 0.f);
+    const T gLNp = vsel(vge(o.LNr, kClamp), G * (vfma(o.LN, p.oma2, o.wL) * o.zL), 0.f);
+#else
     const T gVNp = (G * (vfma(o.VN, p.oma2, o.wV) * o.zV)) * vstep(o.VNr, kClamp, 1.f);   // = -gVNr
     const T gLNp = (G * (vfma(o.LN, p.oma2, o.wL) * o.zL)) * vstep(o.LNr, kClamp, 1.f);   // = -gLNr (specular part)
+#endif
     const T gh = gNHr * g.ih;                                      // n.h = (n.wi + n.wo) ih
     const T cw = gh - gVNp;
     const T ci = vfma(gLN0, vstep(o.LNr, 0.f, 1.f), gh - gLNp);

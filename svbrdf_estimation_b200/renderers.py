@@ -75,10 +75,10 @@ def as_device_maps(svbrdf, what="svbrdf"):
 def host_to_device(t):
     """Host tensor -> current CUDA device (differentiable).  Small tensors and pinned tensors are one copy; large
     pageable tensors go through ``staging.upload`` (pinned double buffer, CPU copy overlapped with the DMA)."""
-    if t.requires_grad or t.numel() * t.element_size() < (8 << 20) or t.is_pinned() or not t.is_contiguous():
+    if t.numel() * t.element_size() < (8 << 20) or t.is_pinned() or not t.is_contiguous():
         return t.cuda(non_blocking=t.is_pinned())
     from . import staging
-    return staging.upload(t)
+    return staging.upload_with_grad(t) if t.requires_grad else staging.upload(t)
 
 
 def as_host_records(records, batch=None):

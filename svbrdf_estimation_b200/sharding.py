@@ -20,9 +20,18 @@ def shard_range(global_batch, rank, world_size):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def _mix64(z):
+    z = (z + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 def shard_seed(seed, rank):
-    """Per-rank seed for the scene sampler, so ranks draw different light/view configurations."""
-    return int(seed) + int(rank)
+    """Per-rank seed for the scene sampler, so ranks draw different light/view configurations.  Seed and rank go
+    through a 64-bit mixer (the splitmix64 finaliser the library's stateless sampler uses): (s, r+1) and (s+1, r)
+    do not collide, as plain ``seed + rank`` would.  63 bits, usable with ``torch.manual_seed``."""
+    return _mix64(_mix64(int(seed) & 0xFFFFFFFFFFFFFFFF) ^ ((int(rank) + 1) * 0xD1342543DE82EF95 & 0xFFFFFFFFFFFFFFFF)) >> 1
 
 
 def global_mean_loss(local_loss, local_batch, group=None):

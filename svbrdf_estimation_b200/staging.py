@@ -49,4 +49,52 @@ def upload(t, device=None):
     return out
 
 
-__all__ = ["upload", "CHUNK_BYTES"]
+def download(t):
+    """CUDA tensor -> new (pageable) CPU tensor, the mirror of :func:`upload`: chunk ``i`` is DMA'd into one pinned buffer
+    while the CPU copies chunk ``i-1`` out of the other.  Blocks until the data is on the host."""
+    if not t.is_cuda:
+        return t
+    t = t.detach().contiguous()
+    out = torch.empty(t.shape, dtype=t.dtype)
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return out
+    src = t.view(-1).view(torch.uint8)
+    dst = out.view(-1).view(torch.uint8)
+    with _lock, torch.cuda.device(t.device):
+        bufs, evs = _buffers(t.device.index)
+        for ev in evs:
+            ev.synchronize()
+        chunks = [(lo, min(CHUNK_BYTES, nbytes - lo)) for lo in range(0, nbytes, CHUNK_BYTES)]
+        for i, (lo, n) in enumerate(chunks):
+            k = i & 1
+            bufs[k][:n].copy_(src[lo:lo + n], non_blocking=True)
+            evs[k].record()
+            if i > 0:
+                plo, pn = chunks[i - 1]
+                evs[1 - k].synchronize()
+                dst[plo:plo + pn].copy_(bufs[1 - k][:pn])
+        plo, pn = chunks[-1]
+        k = (len(chunks) - 1) & 1
+        evs[k].synchronize()
+        dst[plo:plo + pn].copy_(bufs[k][:pn])
+    return out
+
+
+class _StagedUpload(torch.autograd.Function):
+    """Differentiable ``upload``: the gradient travels back through :func:`download`."""
+
+    @staticmethod
+    def forward(ctx, t, device):
+        return upload(t, device)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return download(grad), None
+
+
+def upload_with_grad(t, device=None):
+    return _StagedUpload.apply(t, device)
+
+
+__all__ = ["upload", "download", "upload_with_grad", "CHUNK_BYTES"]

@@ -253,3 +253,90 @@ def test_plain_c_program_through_the_host_entry(env, tmp_path):
     l64, g64 = O.rendering_loss_and_grad(inp.double(), tgt.double(), rec)
     assert abs(c_loss - float(l64)) <= 2e-6 * float(l64)
     assert float((c_grad.double() - g64).norm() / g64.norm()) <= 1e-4
+
+
+def test_channel_layouts_device_and_host(env):
+    """svbrdf_b200_loss_layouts / svbrdf_b200_loss_host: 10-channel maps (roughness stored once) and the 9-channel encoded
+    input with a 10-channel target give the 12-channel results - same loss bits, the single roughness gradient is the sum of
+    the three - on device pointers and through the host pipeline."""
+    lib, _cabi, E = env
+    import svbrdf_estimation_b200 as S
+    B, size, N = 5, 64, 9
+    inp, tgt = synthetic_maps(B, size, 41).cuda(), synthetic_maps(B, size, 42).cuda()
+    torch.manual_seed(3)
+    rec = E.sample_loss_configs(B)
+    to10 = lambda m: torch.cat((m[:, 0:7], m[:, 9:12]), dim=1).contiguous()
+    lin = torch.linspace(-1, 1, size, device="cuda")
+    nbytes = lib.svbrdf_b200_workspace_bytes(B, N, size, size)
+    ws = torch.empty(nbytes // 4 + 1, device="cuda")
+
+    def layouts(a, la, b, lb, l1w, grad):
+        out = torch.zeros(3, device="cuda")
+        g = torch.empty_like(a) if grad else None
+        _cabi.check(lib.svbrdf_b200_loss_layouts(a.data_ptr(), la, b.data_ptr(), lb, B, size, size, rec.data_ptr(), N, l1w,
+                                                 lin.data_ptr(), out.data_ptr(), g.data_ptr() if grad else None, ws.data_ptr(), nbytes, None))
+        torch.cuda.synchronize()
+        return out.cpu(), g
+    o12, g12 = device_loss(lib, _cabi, inp, tgt, rec)
+    o10, g10 = layouts(to10(inp), 10, to10(tgt), 10, -1.0, True)
+    assert float(o10[0]) == float(o12[0])
+    assert torch.equal(g10[:, 0:6], g12[:, 0:6]) and torch.equal(g10[:, 7:10], g12[:, 9:12])
+    assert torch.equal(g10[:, 6], (g12[:, 6] + g12[:, 7]) + g12[:, 8])
+    o10f, _ = layouts(to10(inp), 10, to10(tgt), 10, -1.0, False)
+    assert abs(float(o10f[0]) - float(o12[0])) <= 1e-6 * float(o12[0])
+    # encoded input: 12- vs 10-channel target
+    enc = (torch.rand(B, 9, size, size, device="cuda") * 1.8 - 0.9)
+    oe12, ge12 = layouts(enc, 9, tgt, 12, 0.1, True)
+    oe10, ge10 = layouts(enc, 9, to10(tgt), 10, 0.1, True)
+    assert torch.equal(oe12, oe10) and torch.equal(ge12, ge10)
+    ref = S.mixed_loss_from_encoded(enc, tgt, rec, 0.1)
+    assert abs(float(oe12[0]) - float(ref[0])) <= 1e-6 * float(ref[0])
+    # unsupported combinations are errors
+    out = torch.zeros(3, device="cuda")
+    bad = lib.svbrdf_b200_loss_layouts(inp.data_ptr(), 12, tgt.data_ptr(), 10, B, size, size, rec.data_ptr(), N, -1.0, lin.data_ptr(),
+                                       out.data_ptr(), None, ws.data_ptr(), nbytes, None)
+    assert bad == _cabi.E_INVALID and b"layout" in lib.svbrdf_b200_last_error()
+    assert lib.svbrdf_b200_loss_layouts(enc.data_ptr(), 9, tgt.data_ptr(), 12, B, size, size, rec.data_ptr(), N, -1.0, lin.data_ptr(),
+                                        out.data_ptr(), None, ws.data_ptr(), nbytes, None) == _cabi.E_INVALID
+    # host pipeline, pageable host memory
+    ctx = ctypes.c_void_p()
+    _cabi.check(lib.svbrdf_b200_ctx_create(ctypes.byref(ctx), 8, 9, size, size))
+    try:
+        h_in, h_tg = to10(inp).cpu(), to10(tgt).cpu()
+        h_g = torch.empty_like(h_in)
+        res = (ctypes.c_float * 3)()
+        _cabi.check(lib.svbrdf_b200_loss_host(ctx, h_in.data_ptr(), 10, h_tg.data_ptr(), 10, B, rec.data_ptr(), N, -1.0, res, h_g.data_ptr()))
+        assert res[0] == float(o12[0]) and torch.equal(h_g, g10.cpu())
+        h_e, h_ge = enc.cpu(), torch.empty(B, 9, size, size)
+        _cabi.check(lib.svbrdf_b200_loss_host(ctx, h_e.data_ptr(), 9, h_tg.data_ptr(), 10, B, rec.data_ptr(), N, 0.1, res, h_ge.data_ptr()))
+        assert res[0] == float(oe10[0]) and res[1] == float(oe10[1]) and torch.equal(h_ge, ge10.cpu())
+    finally:
+        lib.svbrdf_b200_ctx_destroy(ctx)
+
+
+def test_pageable_host_tensors_through_the_python_api(env):
+    """RenderingLoss on large pageable CPU tensors (what a caller without device tensors does): staged through pinned
+    double buffers both ways (staging.upload / download); same result as the device path."""
+    import svbrdf_estimation_b200 as S
+    from svbrdf_estimation_b200 import staging
+    lib, _cabi, E = env
+    B, size = 6, 256                                     # 18.9 MB per tensor: above the staging threshold, several chunks with a small chunk size
+    inp, tgt = synthetic_maps(B, size, 51), synthetic_maps(B, size, 52)
+    rec = E.sample_loss_configs(B)
+    old = staging.CHUNK_BYTES
+    staging.CHUNK_BYTES = 5 << 20
+    staging._state.clear()
+    try:
+        x = inp.clone().requires_grad_(True)
+        loss = S.rendering_loss_with_records(x, tgt, rec)
+        loss.backward()
+        assert loss.device.type == "cpu" and x.grad.device.type == "cpu"
+        xd = inp.cuda().requires_grad_(True)
+        ld = S.rendering_loss_with_records(xd, tgt.cuda(), rec)
+        ld.backward()
+        assert float(loss) == float(ld) and torch.equal(x.grad, xd.grad.cpu())
+        t = torch.rand(3_000_001)
+        assert torch.equal(staging.download(staging.upload(t)), t)
+    finally:
+        staging.CHUNK_BYTES = old
+        staging._state.clear()
