@@ -1,6 +1,6 @@
 """TEST / BENCH INFRASTRUCTURE.  Compiles the UNMODIFIED reference modules of the hot path to Python bytecode:
 
-    /root/reference/development/multiImage_pytorch/{utils,environment,renderers,losses}.py  ->  oracle/_ref/*.pyc
+    /root/reference/development/multiImage_pytorch/{utils,environment,renderers,losses}.py  ->  oracle/_ref/*.bin
 
 ``oracle/_ref/`` is git-ignored (no reference source or derivative enters the history) but travels to the GPU box with
 the snapshot, like the built ``.so`` files, so ``bench.py --impl reference`` and the ``cpu_baseline`` leg can time the
@@ -26,7 +26,7 @@ def build(reference=REFERENCE, out=OUT):
     written = []
     for name in MODULES:
         src = os.path.join(reference, name + ".py")
-        dst = os.path.join(out, name + ".pyc")
+        dst = os.path.join(out, name + ".bin")
         py_compile.compile(src, cfile=dst, dfile="reference/%s.py" % name, doraise=True, optimize=0)
         written.append(dst)
     with open(os.path.join(out, "PYTHON_VERSION"), "w") as f:

@@ -20,7 +20,7 @@ def available():
                 return False
     except OSError:
         return False
-    return all(os.path.exists(os.path.join(REF, m + ".pyc")) for m in ("utils", "environment", "renderers", "losses"))
+    return all(os.path.exists(os.path.join(REF, m + ".bin")) for m in ("utils", "environment", "renderers", "losses"))
 
 
 def load():
@@ -41,7 +41,7 @@ def load():
         except Exception:
             sys.modules["cv2"] = types.ModuleType("cv2")
         for n in names:
-            loader = importlib.machinery.SourcelessFileLoader(n, os.path.join(REF, n + ".pyc"))
+            loader = importlib.machinery.SourcelessFileLoader(n, os.path.join(REF, n + ".bin"))
             spec = importlib.util.spec_from_loader(n, loader)
             m = importlib.util.module_from_spec(spec)
             sys.modules[n] = m                      # the reference's modules import each other by bare name

@@ -96,6 +96,16 @@ def main():
                 r64t = O.render_batch(tgt.double().to(dev), cfg).cpu().numpy()
             rows.append(report("oracle-on-gpu:" + name, inp.numpy(), tgt.numpy(), cfg.numpy(), float(l32), g32.cpu().numpy(), r32,
                                float(l64), g64.cpu().numpy(), r64, r64t))
+            # term-level treatment of the L1 sign (tests/parity.py flipped_term_analysis): which individual terms did the
+            # kernels - and the reference's own fp32 run - take with the other sign, and what is left once only those are put back
+            _, grad, _ = ours(inp.numpy(), tgt.numpy(), cfg.numpy())
+            for who, g in (("ours", grad), ("ref32", g32.cpu().numpy())):
+                res = parity.flipped_term_analysis(O, inp, tgt, cfg, g, device=dev)
+                rows[-1]["flipped_terms_" + who] = {
+                    "candidates_0<|l|<1e-3": res["candidates"], "terms": res["terms"], "flipped": res["flipped"],
+                    "max_abs_l_of_a_flipped_term": res["max_abs_l_flipped"],
+                    "rel_l2_vs_ref64_all_pixels_raw": {gn: parity.rel_l2(res["g_ours"][:, s], res["g64"][:, s]) for gn, s in parity.GROUPS},
+                    "rel_l2_vs_ref64_all_pixels_flipped_terms_put_back": {gn: parity.rel_l2(res["g_corrected"][:, s], res["g64"][:, s]) for gn, s in parity.GROUPS}}
             torch.cuda.empty_cache()
     print(json.dumps(rows, indent=1))
 

@@ -39,8 +39,15 @@ def rf_cycles(body):
     return total
 
 
+# the kernel RenderingLoss fwd+bwd launches on every power-of-two map size: packed lanes, BWD, grey lights, 12-channel
+# layout, large parameter block, default accuracy, per-warp row table
+DEFAULT_KERNEL = r"loss_kernel_packedINS_2F2ELb1ELb0ELb1ELi0ELi900ELb0ELb1EEE"
+
+
 def main():
-    pat = re.compile(sys.argv[1] if len(sys.argv) > 1 else r"loss_kernelINS_2F2ELb1ELb0ELb1ELb0ELi900")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    as_json = "--json" in sys.argv
+    pat = re.compile(args[0] if args else DEFAULT_KERNEL)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     extra = os.environ.get("SVB_EXTRA_FLAGS", "").split()        # e.g. SVB_EXTRA_FLAGS="-DSVB_F2_MINB=2" for experiments
     p = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"] + extra +
@@ -73,6 +80,18 @@ def main():
                 m = re.search(r"0x([0-9a-f]+)", args)
                 if m and int(m.group(1), 16) in addr and addr[int(m.group(1), 16)] < i:
                     loops.append((addr[int(m.group(1), 16)], i))
+        if as_json:
+            import json
+            s0, e0 = [l for l in loops if any(op.startswith('MUFU') for _, op, _ in ins[l[0]:l[1] + 1])][0]   # first loop with MUFU work: the shared-roughness record loop
+            body = ins[s0:e0 + 1]
+            mix = collections.Counter(op.split(".")[0] for _, op, _ in body)
+            packed_fma, packed_other = mix.get("FFMA2", 0), mix.get("FMUL2", 0) + mix.get("FADD2", 0)
+            flop_pair = 4 * packed_fma + 2 * packed_other + 2 * mix.get("FFMA", 0) + mix.get("FMUL", 0) + mix.get("FADD", 0)
+            print(json.dumps({"kernel": name, "registers": regs.get(name, (0, ""))[0], "instructions_total": len(ins),
+                              "record_loop_instructions": len(body), "record_loop_mix": dict(mix.most_common()),
+                              "executed_flop_per_eval": flop_pair / 2.0, "mufu_per_eval": mix.get("MUFU", 0) / 2.0,
+                              "register_file_cycles_model": rf_cycles(body)}))
+            continue
         print("== %s: %d registers, %d instructions total" % (name[:110], regs.get(name, (0, ""))[0], len(ins)))
         for (s, e) in loops:
             body = ins[s:e + 1]

@@ -196,8 +196,9 @@ extern __shared__ float4 svb_rowtab[];
 
 // The per-thread work of the loss kernels (both lane types).  Register budget: the packed kernels are capped at 160
 // registers per thread with __maxnreg__ (3 CTAs of 128 threads per SM would allow 168; ptxas settles on 158 and finds
-// a 2 % faster schedule there - measured on B200 for caps 144 ... 168, profiles/r2_variants.txt), the
-// one-pixel-per-thread kernels at 128 (2 CTAs of 256 threads).
+// a 2 % faster schedule there - measured on B200 for caps 144 ... 168, profiles/r2_variants.txt; the MixedLoss,
+// encoded-input and accurate kernels keep 168, they spill below), the one-pixel-per-thread kernels at 128 (2 CTAs of
+// 256 threads).
 template <typename T, bool BWD, bool MIXED, bool GREY, int LAY, int CAP, bool ACC, bool ROWTAB>
 __device__ __forceinline__ void loss_body(const LossArgs& a, const SceneBlock<CAP>& sc) {
     constexpr int THREADS = Cfg<T>::kThreads;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void loss_body(const LossArgs& a, const SceneBlock<CA
 #define SVB_LOSS_MAXNREG 160
 #endif
 template <typename T, bool BWD, bool MIXED, bool GREY, int LAY, int CAP, bool ACC = false, bool ROWTAB = false>
-__global__ void __maxnreg__(SVB_LOSS_MAXNREG)
+__global__ void __maxnreg__((MIXED || LAY != kLay12 || ACC) ? 168 : SVB_LOSS_MAXNREG)
 loss_kernel_packed(const LossArgs a, const __grid_constant__ SceneBlock<CAP> sc) {
     loss_body<T, BWD, MIXED, GREY, LAY, CAP, ACC, ROWTAB>(a, sc);
 }
