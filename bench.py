@@ -670,7 +670,7 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        val, sec, b, threads, kind = time_cpu_port(args.workload, 5, 1, budget_s=40.0, full_batch=True)
+        val, sec, b, threads, kind = time_cpu_port(args.workload, 5, 1, budget_s=70.0, full_batch=True)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": "%s, %dx%d, N=%d, 1 warm-up + 5 timed fwd+bwd passes (%.2f s each)"
                          % ("the whole batch of the workload (%d maps)" % B if b == B else "first %d of %d maps of the workload" % (b, B),

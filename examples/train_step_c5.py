@@ -6,9 +6,9 @@ global batch sharded over the GPUs of one box, CNN gradients all-reduced by Dist
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 \
         examples/train_step_c5.py --batch-per-gpu 32
 
-The network is a stand-in: a pix2pix-style 8-down / 8-up U-Net with instance norm that emits the reference's
-9-channel encoding (the reference's ``models.py`` is out of scope for this repository and is used unchanged by
-its own training script).  What this script shows is the hot path in its real position:
+The network is a stand-in of the reference generator's shape and size (examples/unet_standin.py, 79.99 M parameters;
+the reference's ``models.py`` is out of scope for this repository and is used unchanged by its own training script;
+see INTEGRATION.md).  ``bench.py`` runs the same step as its ``train_step_c5`` leg with the GLOBAL batch fixed at 256.  What this script shows is the hot path in its real position:
 ``tanh(generator(x))`` goes straight into ``MixedLoss.forward_encoded`` (decode + map-L1 + rendering loss + their
 gradient in one kernel), each rank samples the scenes of its own batch slice (``NativeSceneSampler`` keyed by the
 global sample index), and the only traffic over NVLink is DDP's gradient all-reduce.
@@ -24,53 +24,11 @@ import torch.distributed as dist
 import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import svbrdf_estimation_b200 as S                                 # noqa: E402
+from svbrdf_estimation_b200 import sharding                        # noqa: E402
 from svbrdf_estimation_b200.environment import NativeSceneSampler  # noqa: E402
-
-
-class Down(nn.Module):
-    def __init__(self, cin, cout, norm=True):
-        super().__init__()
-        self.conv = nn.Conv2d(cin, cout, 4, 2, 1)
-        self.norm = nn.InstanceNorm2d(cout, affine=True) if norm else nn.Identity()
-
-    def forward(self, x):
-        return self.norm(self.conv(nn.functional.leaky_relu(x, 0.2)))
-
-
-class Up(nn.Module):
-    def __init__(self, cin, cout):
-        super().__init__()
-        self.conv = nn.ConvTranspose2d(cin, cout, 4, 2, 1)
-        self.norm = nn.InstanceNorm2d(cout, affine=True)
-
-    def forward(self, x):
-        return self.norm(self.conv(nn.functional.relu(x)))
-
-
-class UNetStandIn(nn.Module):
-    """3 -> 9 channels, 8 stride-2 encoders and 8 decoders with skip connections (for 256x256 inputs)."""
-
-    def __init__(self, ngf=64, depth=8):
-        super().__init__()
-        ch = [min(ngf * 2 ** i, ngf * 8) for i in range(depth)]
-        self.first = nn.Conv2d(3, ch[0], 4, 2, 1)
-        self.downs = nn.ModuleList([Down(ch[i], ch[i + 1], norm=(i + 1 < depth - 1)) for i in range(depth - 1)])
-        ups = []
-        for i in range(depth - 1, 0, -1):
-            ups.append(Up(ch[i] * (1 if i == depth - 1 else 2), ch[i - 1]))
-        self.ups = nn.ModuleList(ups)
-        self.last = nn.ConvTranspose2d(ch[0] * 2, 9, 4, 2, 1)
-
-    def forward(self, x):
-        feats = [self.first(x)]
-        for d in self.downs:
-            feats.append(d(feats[-1]))
-        y = feats[-1]
-        for i, u in enumerate(self.ups):
-            y = u(y)
-            y = torch.cat((y, feats[-2 - i]), dim=1)
-        return torch.tanh(self.last(nn.functional.relu(y)))       # the 9-channel encoding in [-1,1] (models.py:336-338)
+from unet_standin import UNetStandIn                               # noqa: E402
 
 
 def main():
@@ -86,13 +44,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(313)
-    model = UNetStandIn(depth=8 if args.size >= 256 else max(3, args.size.bit_length() - 1)).to(dev)
+    model = UNetStandIn().to(dev)
     n_params = sum(p.numel() for p in model.parameters())
-    net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    net = nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
     opt = torch.optim.Adam(net.parameters(), lr=1e-5)                                    # main.py:74
     B = args.batch_per_gpu
+    lo, hi = sharding.shard_range(B * world, rank, world)            # this rank's slice of the global batch
     loss_fn = S.MixedLoss(S.LocalRenderer(), l1_weight=0.1,
-                          scene_sampler=NativeSceneSampler(seed=313, first_batch_element=rank * B))
+                          scene_sampler=NativeSceneSampler(seed=313, first_batch_element=lo))
     g = torch.Generator("cpu").manual_seed(1000 + rank)
     images = torch.rand(B, 3, args.size, args.size, generator=g).to(dev)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -119,7 +78,7 @@ def main():
         if it >= args.warmup:
             step_ms.append((time.perf_counter() - t0) * 1e3)
             loss_ms.append(ev[1].elapsed_time(ev[2]))
-            losses.append(float(loss.detach()))
+            losses.append(float(sharding.global_mean_loss(loss.detach(), B)))     # NCCL all-reduce of the scalar, for logging
     t = torch.tensor([sum(step_ms) / len(step_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -47,7 +47,7 @@ template <typename T>
 SVB_DEV typename LaneTraits<T>::Mask rough_differs(T ra, T rb) { return vne(vmax(ra, kClamp), vmax(rb, kClamp)); }
 template <typename T>
 SVB_DEV typename LaneTraits<T>::Mask albedo_differs(T da, T sa, T db, T sb) {
-    return mor(vne(sa, sb), mand(vne(da, db), mor(vne1(sa), vne1(sb))));
+    return mor(vne(sa, sb), mand(vne(da, db), vne1(sa)));      // second clause only matters when sa == sb
 }
 SVB_DEV bool all_or_none(bool a, bool b, bool c) { return (a == b) && (b == c); }
 SVB_DEV bool all_or_none(B2 a, B2 b, B2 c) { return (a.x == b.x) && (b.x == c.x) && (a.y == b.y) && (b.y == c.y); }

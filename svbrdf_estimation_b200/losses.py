@@ -33,6 +33,23 @@ def _check_pair(input, target):
         raise ValueError("input and target are on different devices")
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on_device(device):
+    """The C ABI works on the CURRENT CUDA device: switch only when the tensors live elsewhere (the context manager
+    costs more host time than the launch it guards)."""
+    return _NO_SWITCH if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+
 def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded=False, accurate=False):
     """One C-ABI loss call on the current stream of ``b``'s device.  ``a`` is the differentiated argument
     ([B,12,H,W] maps, or the [B,9,H,W] encoded network output when ``encoded``), ``grad`` its gradient buffer
@@ -41,7 +58,7 @@ def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded
     B, _, H, W = b.shape
     N = records.shape[1]
     gp = grad.data_ptr() if grad is not None else None
-    with torch.cuda.device(b.device):
+    with _on_device(b.device):
         stream = torch.cuda.current_stream().cuda_stream
         if encoded:
             status = lib.svbrdf_b200_mixed_loss_encoded_forward_backward(
@@ -60,14 +77,11 @@ def _launch_loss(a, b, records, l1_weight, out, grad, ws, ws_bytes, lin, encoded
                 status = lib.svbrdf_b200_loss_forward_accurate(
                     a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
                     ws.data_ptr(), ws_bytes, stream)
-        elif grad is not None:
-            status = lib.svbrdf_b200_loss_forward_backward(
-                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(), gp,
-                ws.data_ptr(), ws_bytes, stream)
         else:
-            status = lib.svbrdf_b200_loss_forward(
-                a.data_ptr(), b.data_ptr(), B, H, W, records.data_ptr(), N, lin.data_ptr(), out.data_ptr(),
-                ws.data_ptr(), ws_bytes, stream)
+            # RenderingLoss, forward (+ backward when grad is given); writes out[0..2] = loss, loss, 0
+            status = lib.svbrdf_b200_loss_layouts(
+                a.data_ptr(), _cabi.LAYOUT_MAPS12, b.data_ptr(), _cabi.LAYOUT_MAPS12, B, H, W, records.data_ptr(), N, -1.0,
+                lin.data_ptr(), out.data_ptr(), gp, ws.data_ptr(), ws_bytes, stream)
     _cabi.check(status)
 
 
@@ -105,8 +119,8 @@ class _FusedLoss(torch.autograd.Function):
         ctx.grads = (grad_in if want_in else None, grad_tg) if eager else None
         ctx.save_for_backward(input, target)
         ctx.records, ctx.meta = records, (l1_weight, encoded, accurate)
-        loss, parts = out[0].reshape(()), out[1:3]
-        if l1_weight is None:
+        loss, parts = out[0].reshape(()), out[1:3]        # the finalize kernel writes all three values (map-L1 = 0 for RenderingLoss)
+        if accurate:                                      # the accurate entry points write the loss only
             parts = torch.stack((loss.detach(), torch.zeros_like(loss)))
         ctx.mark_non_differentiable(parts)
         return loss, parts
@@ -136,7 +150,7 @@ class _FusedLoss(torch.autograd.Function):
         lib = _cabi.lib()
         for g in grads:
             if g is not None:
-                with torch.cuda.device(g.device):
+                with _on_device(g.device):
                     # in place; returns on the device when the upstream gradient is 1 (no host sync)
                     _cabi.check(lib.svbrdf_b200_scale_grad(g.data_ptr(), g.numel(), up.data_ptr(),
                                                            torch.cuda.current_stream().cuda_stream))

@@ -83,7 +83,11 @@ def host_to_device(t):
 
 def as_host_records(records, batch=None):
     """-> contiguous float32 CPU tensor [N,9] or [B,N,9]."""
-    rec = torch.as_tensor(records).detach().to(device="cpu", dtype=torch.float32).contiguous()
+    if isinstance(records, torch.Tensor) and records.device.type == "cpu" and records.dtype == torch.float32 \
+            and records.is_contiguous() and not records.requires_grad:
+        rec = records
+    else:
+        rec = torch.as_tensor(records).detach().to(device="cpu", dtype=torch.float32).contiguous()
     if rec.dim() not in (2, 3) or rec.shape[-1] != 9 or rec.shape[-2] == 0:
         raise ValueError("scene records must have shape [N,9] or [B,N,9], got %s" % (tuple(rec.shape),))
     if rec.dim() == 3 and batch is not None and rec.shape[0] != batch:
