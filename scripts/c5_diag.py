@@ -24,15 +24,20 @@ def run(B, channels_last=False, graph=False, prof=False):
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)
+    net = model
     loss_fn = S.MixedLoss(S.LocalRenderer(), scene_sampler=NativeSceneSampler(313))
     images = torch.rand(B, 3, 256, 256, device=dev)
     if channels_last:
         images = images.contiguous(memory_format=torch.channels_last)
     target = bench.synthetic_maps(min(B, 32), 256, 5000).repeat((B + 31) // 32, 1, 1, 1)[:B].to(dev).contiguous()
 
+    if graph:
+        # forward and backward of the network as two CUDA graphs (the loss stays outside: fresh scenes per step)
+        net = torch.cuda.make_graphed_callables(model, (images,), num_warmup_iters=3)
+
     def step():
-        opt.zero_grad(set_to_none=True)
-        enc = model(images)
+        opt.zero_grad(set_to_none=not graph)
+        enc = net(images)
         loss = loss_fn.forward_encoded(enc.contiguous(), target)
         loss.backward()
         opt.step()
@@ -45,7 +50,7 @@ def run(B, channels_last=False, graph=False, prof=False):
         step()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / n * 1e3
-    out = "B=%d channels_last=%s: %.2f ms/step (%.3f ms/sample)" % (B, channels_last, ms, ms / B)
+    out = "B=%d channels_last=%s graph=%s: %.2f ms/step (%.3f ms/sample)" % (B, channels_last, graph, ms, ms / B)
     if prof:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
@@ -63,7 +68,14 @@ def run(B, channels_last=False, graph=False, prof=False):
 
 
 if __name__ == "__main__":
-    run(32, prof=True)
-    run(256, prof=True)
-    run(32, channels_last=True)
-    run(256, channels_last=True)
+    if "--graph" in sys.argv:
+        run(32)
+        run(32, graph=True)
+        run(64)
+        run(64, graph=True)
+        run(256)
+        run(256, graph=True)
+    else:
+        run(32, prof=True)
+        run(256, prof=True)
+        run(32, channels_last=True)
