@@ -582,7 +582,16 @@ def run_ours(args):
                 api_step()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / n_api
-            pageable = {"value": evals_per_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_api,
+            # what the same tensors cost with torch's own blocking pageable copies (no kernel): tensor.cuda() x2, grad.cpu()
+            gdev = torch.empty(B, 12, size, size, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                host_in.cuda(); host_tg.cuda(); gdev.cpu()
+            torch.cuda.synchronize()
+            plain_ms = (time.perf_counter() - t0) / 3 * 1e3
+            del gdev
+            pageable = {"torch_blocking_pageable_copies_alone_ms": plain_ms,"value": evals_per_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_api,
                         "call": "RenderingLoss(LocalRenderer())(cpu_input, cpu_target).backward() with pageable [64,12,256,256] CPU tensors "
                                 "(renderers.host_to_device -> staging.upload / download: 32 MB pinned double buffers)",
                         "h2d_bytes_per_step": 2 * host_in.numel() * 4, "d2h_bytes_per_step": host_in.numel() * 4 + 4}
