@@ -20,7 +20,7 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 worst = {"loss": 0.0, "grad": 0.0, "render": 0.0, "rgrad": 0.0}
 for i in range(cases):
-    W = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 32, 33, 48, 63, 64, 65, 70]))
+    W = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 32, 33, 48, 63, 64, 64, 65, 70, 128]))
     B, nr, ns = int(rng.integers(1, 5)), int(rng.integers(0, 12)), int(rng.integers(0, 19))
     if nr + ns == 0:
         nr = 1

@@ -340,3 +340,32 @@ def test_pageable_host_tensors_through_the_python_api(env):
     finally:
         staging.CHUNK_BYTES = old
         staging._state.clear()
+
+
+def test_bench_line_contract(env):
+    """`python bench.py` prints ONE JSON line with the contract's keys; roofline / e2e / train_step_c5 objects are filled from
+    live measurements (short run: 5 steps, a global batch of 8 for the configs[4] leg)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+                          "--c5-global-batch", "8", "--c5-steps", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["unit"] == "G evals/s" and d["value"] > 50 and d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f32" and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "c2" and d["gpu_launches"] == 10
+    r = d["roofline"]
+    assert r["bound"] == "fp32" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.3 < r["frac"] < 1.0
+    assert r["traffic"] is None or 0.5 * 604e6 < r["traffic"] < 1.5 * 604e6
+    assert d["executed_work"]["sass_model_matches_this_build"] is True and d["executed_work"]["flop_per_eval_executed"] > 100
+    e = d["e2e"]
+    assert e["value"] > 1 and e["h2d_bytes_per_step"] == 2 * 64 * 10 * 256 * 256 * 4 and e["d2h_bytes_per_step"] == 64 * 10 * 256 * 256 * 4 + 12
+    assert e["matches_device_entry"] is True and e["maps12_variant"]["h2d_bytes_per_step"] == 2 * 64 * 12 * 256 * 256 * 4
+    assert e["python_api_pageable_tensors"]["value"] > 0.1
+    c = d["train_step_c5"]
+    assert c["global_batch"] == 8 and c["step_ms"] > 0 and 79 < c["params_M"] < 81 and c["scaling"] == "strong"
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
