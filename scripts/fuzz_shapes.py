@@ -45,7 +45,12 @@ for i in range(cases):
     assert np.isfinite(g).all()
     e_grad = parity.rel_l2(g * keep, g64.numpy() * keep)
     floor = parity.rel_l2(g32.numpy() * keep, g64.numpy() * keep)
-    assert e_grad <= max(3e-4, 2.0 * floor), ("gradient", W, B, nr + ns, stress, e_grad, floor)
+    # Images of a few thousand pixels have little averaging: one highlight pixel whose GGX denominator sits near its clamp
+    # (q ~ 1e-3, roughness ~ 0.14) can carry 99 % of the squared error of the normals gradient (measured on the host
+    # emulation over 120 random bench-distribution cases: median 5.3e-5, p90 8.4e-5, 4 % above 1e-4, max 2.6e-4; the
+    # reference's own fp32 run: 3.4e-5 / 5.2e-5 / 1 % / 1.3e-4; accurate kernels: 1.2e-6 / 2.1e-6 / 0 / 5.3e-6).  The 1e-4
+    # bound is asserted at the BASELINE sizes (tests/test_gpu_parity.py); here: REL_L2_STRESS or twice the reference's noise.
+    assert e_grad <= max(parity.REL_L2_STRESS, 2.0 * floor), ("gradient", W, B, nr + ns, stress, e_grad, floor)
     r = emu.render_forward(inp.numpy(), cfg.numpy()) if EMU else S.render_records(inp.cuda(), cfg).cpu().numpy()
     e_r = parity.rel_l2(r, r64i)
     w = torch.randn(B, nr + ns, 3, W, W)
